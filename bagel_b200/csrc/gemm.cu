@@ -1,0 +1,370 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+// Replaces every nn.Linear on BAGEL's forward path (reference: modeling/bagel/qwen2_navit.py:515-517,
+// 529-536, 589-594; modeling/qwen2/modeling_qwen2.py:200-201; modeling/bagel/bagel.py:801-833), which
+// the reference runs as cuBLASLt GEMM + separate ATen elementwise launches.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, kStages-deep smem ring)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma 128 x BN x 16, fp32 accum in TMEM)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile
+// i+1. A and W are both K-major ("TN" GEMM: nn.Linear weight layout), fp32 accumulation, bf16 output.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace bagel {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom along K
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kGroupM = 16;  // rasterisation: 16 M-tiles share a column sweep (L2 reuse of W panels)
+
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,    // C = bf16(acc + bias)
+  EPI_RESID = 1,   // C = bf16(resid + bf16(acc + bias))                (o_proj / down_proj + residual add)
+  EPI_SWIGLU = 2,  // C[:, j] = bf16(bf16(silu(bf16 g_j)) * bf16 u_j); W rows interleaved per 256 (128 g | 128 u)
+  EPI_GELU = 3,    // C = bf16(gelu_tanh(bf16(acc + bias)))             (SigLIP MLP / connector)
+  EPI_SILU = 4,    // C = bf16(silu(bf16(acc + bias)))                  (timestep MLP)
+};
+
+struct GemmParams {
+  int M, N, K;
+  __nv_bfloat16* C;
+  long long ldc;
+  const __nv_bfloat16* bias;   // [N] or null
+  const __nv_bfloat16* resid;  // [*, ldr] or null (EPI_RESID)
+  long long ldr;
+  const int* row_map;  // optional: output (and residual) row of A-row r is row_map[r]
+  int num_m, num_n, num_tiles;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int group_size = kGroupM * num_n;
+  const int g = tile / group_size;
+  const int first_m = g * kGroupM;
+  const int gm = min(num_m - first_m, kGroupM);
+  const int local = tile - g * group_size;
+  m_blk = first_m + local % gm;
+  n_blk = local / gm;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // torch "gelu_pytorch_tanh": 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  static_assert(EPI != EPI_SWIGLU || BN == 256, "SwiGLU epilogue pairs 128 gate + 128 up columns");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, kEvictNormal);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN, kEvictNormal);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr>>4) field
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+      const int row = m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      long long out_row = row;
+      if (p.row_map != nullptr && row_ok) out_row = p.row_map[row];
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
+
+      if constexpr (EPI == EPI_SWIGLU) {
+        const int n_out0 = n_blk * (BN / 2);
+        __nv_bfloat16* crow = p.C + out_row * p.ldc + n_out0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld_x32(t_acc + c * 32, g);
+          tmem_ld_x32(t_acc + 128 + c * 32, u);
+          tmem_ld_wait();
+          if (row_ok) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float h0, h1;
+              {
+                const float gg = bf16_round(__uint_as_float(g[2 * j]));
+                const float uu = bf16_round(__uint_as_float(u[2 * j]));
+                h0 = bf16_round(silu_f(gg)) * uu;
+              }
+              {
+                const float gg = bf16_round(__uint_as_float(g[2 * j + 1]));
+                const float uu = bf16_round(__uint_as_float(u[2 * j + 1]));
+                h1 = bf16_round(silu_f(gg)) * uu;
+              }
+              o[j] = pack_bf16x2(h0, h1);
+            }
+            const int n0 = n_out0 + c * 32;
+            if (n0 + 32 <= p.N / 2) {
+              uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + 2 * j < p.N / 2) *reinterpret_cast<uint32_t*>(crow + c * 32 + 2 * j) = o[j];
+            }
+          }
+        }
+      } else {
+        const int n0_tile = n_blk * BN;
+        __nv_bfloat16* crow = p.C + out_row * p.ldc + n0_tile;
+        const __nv_bfloat16* rrow = (EPI == EPI_RESID) ? p.resid + out_row * p.ldr + n0_tile : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n0_tile + c * 32;
+          if (row_ok && n0 < p.N) {
+            const bool full = (n0 + 32 <= p.N);
+            uint32_t rr[16];
+            if constexpr (EPI == EPI_RESID) {
+              if (full) {
+                const uint4* src = reinterpret_cast<const uint4*>(rrow + c * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 t = src[q];
+                  rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  rr[j] = (n0 + 2 * j < p.N) ? *reinterpret_cast<const uint32_t*>(rrow + c * 32 + 2 * j) : 0u;
+              }
+            }
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x0 = __uint_as_float(v[2 * j]);
+              float x1 = __uint_as_float(v[2 * j + 1]);
+              if (p.bias != nullptr) {
+                const int nb = min(n0 + 2 * j, p.N - 2);
+                const uint32_t bb = *reinterpret_cast<const uint32_t*>(p.bias + nb);
+                x0 += bf16_lo(bb);
+                x1 += bf16_hi(bb);
+              }
+              if constexpr (EPI == EPI_RESID) {
+                x0 = bf16_lo(rr[j]) + bf16_round(x0);
+                x1 = bf16_hi(rr[j]) + bf16_round(x1);
+              } else if constexpr (EPI == EPI_GELU) {
+                x0 = gelu_tanh_f(bf16_round(x0));
+                x1 = gelu_tanh_f(bf16_round(x1));
+              } else if constexpr (EPI == EPI_SILU) {
+                x0 = silu_f(bf16_round(x0));
+                x1 = silu_f(bf16_round(x1));
+              }
+              o[j] = pack_bf16x2(x0, x1);
+            }
+            if (full) {
+              uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + 2 * j < p.N) *reinterpret_cast<uint32_t*>(crow + c * 32 + 2 * j) = o[j];
+            }
+          }
+        }
+      }
+      // all of this warp's tcgen05.ld have completed (wait::ld above) -> hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool attr_done = false;  // per-instantiation; idempotent if raced
+  if (!attr_done) {
+    BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  p.num_m = (p.M + BM - 1) / BM;
+  p.num_n = (p.N + BN - 1) / BN;
+  p.num_tiles = p.num_m * p.num_n;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                        cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, p, s);
+    case EPI_RESID: return launch_gemm<BN, EPI_RESID>(tmA, tmB, p, s);
+    case EPI_GELU: return launch_gemm<BN, EPI_GELU>(tmA, tmB, p, s);
+    case EPI_SILU: return launch_gemm<BN, EPI_SILU>(tmA, tmB, p, s);
+    default: return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: unknown epilogue %d", epi);
+  }
+}
+
+}  // namespace bagel
+
+using namespace bagel;
+
+extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                               int M, int N, int K, const void* bias, const void* resid, long long ldr,
+                               const int* row_map, int epilogue, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(BAGEL_ERR_SHAPE, "bagel_gemm_bf16: M,N,K must be > 0");
+  if ((lda % 8) || (ldw % 8) || (ldc % 8) || (K % 8) || (N % 8))
+    return set_error(BAGEL_ERR_ALIGN, "bagel_gemm_bf16: K, N and leading dims must be multiples of 8 (16 B)");
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)bias | (uintptr_t)resid) & 15)
+    return set_error(BAGEL_ERR_ALIGN, "bagel_gemm_bf16: pointers must be 16-byte aligned");
+  if (epilogue == EPI_RESID && (resid == nullptr || (ldr % 8)))
+    return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: EPI_RESID needs resid with ldr %% 8 == 0");
+  if (int rc = require_sm100()) return rc;
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = static_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.ldr = ldr;
+  p.row_map = row_map;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  int bn;
+  if (epilogue == EPI_SWIGLU) {
+    if (N % 256) return set_error(BAGEL_ERR_SHAPE, "bagel_gemm_bf16: SwiGLU needs N (=2*I, interleaved) %% 256 == 0");
+    bn = 256;
+  } else {
+    bn = (N % 256 == 0 || N >= 1024) ? 256 : (N > 64 ? 128 : 64);
+  }
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, bn)) return rc;
+
+  if (epilogue == EPI_SWIGLU) return launch_gemm<256, EPI_SWIGLU>(tmA, tmB, p, s);
+  if (bn == 256) return dispatch_epi<256>(epilogue, tmA, tmB, p, s);
+  if (bn == 128) return dispatch_epi<128>(epilogue, tmA, tmB, p, s);
+  return dispatch_epi<64>(epilogue, tmA, tmB, p, s);
+}

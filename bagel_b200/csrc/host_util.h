@@ -1,0 +1,32 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, device queries, TMA descriptors.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/bagel_b200.h"
+
+namespace bagel {
+
+extern std::atomic<long long> g_launches;       // kernels launched by this library (bagel_launch_count)
+int set_error(int code, const char* fmt, ...);  // records thread-local message, returns `code`
+int sm_count();                                 // SMs of the current device (cached per device)
+int require_sm100();                            // 0 if current device is sm_100, else BAGEL_ERR_ARCH
+// 2D bf16 tensor map: global [rows, cols] with row pitch `ld` elements; box [box_rows, box_cols];
+// 128-byte swizzle; out-of-bounds reads are zero-filled.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows);
+
+#define BAGEL_CUDA_CHECK(expr)                                                                       \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::bagel::set_error(BAGEL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                                 \
+  } while (0)
+
+}  // namespace bagel

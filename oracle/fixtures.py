@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE — deterministic synthetic weights / inputs shared by the golden generator, the tests,
+smoke() and bench.py. Nothing here reads /root/reference; tensors come from seeded CPU generators so the
+same bits are produced in this container and on the GPU box (same torch build).
+
+Random init follows the reference's recipe in spirit (normal weights, modeling_qwen2.py:563-572) but also
+randomises norm weights and biases — with the stock init (ones / zeros) those code paths would be
+untested — and gives llm2vae non-zero weights (the reference zero-inits it, bagel.py:96-99, which makes
+v_t constant).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .qwen2_mot import LMConfig
+
+TINY_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                   num_key_value_heads=2, vocab_size=1024)            # BASELINE.json configs[0]
+TINY128_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=1, vocab_size=1024)         # same but head_dim 128 (7B's head_dim)
+BAGEL_7B_LM = LMConfig(hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
+                       num_key_value_heads=4, vocab_size=152064)      # BAGEL-7B-MoT llm_config.json
+
+
+def _normal(gen, shape, std):
+    return torch.randn(shape, generator=gen, dtype=torch.float32) * std
+
+
+def lm_state_dict(cfg: LMConfig, seed: int = 0, dtype=torch.bfloat16, w_std: float = 0.05,
+                  lm_head: bool = True) -> Dict[str, torch.Tensor]:
+    """Reference key names (qwen2_navit.py Qwen2ForCausalLM state_dict), MoT layers."""
+    g = torch.Generator().manual_seed(seed)
+    H, I, d = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+    Hq, Hk = cfg.num_attention_heads, cfg.num_key_value_heads
+    sd = {"model.embed_tokens.weight": _normal(g, (cfg.vocab_size, H), 1.0)}
+    for li in range(cfg.num_hidden_layers):
+        p = f"model.layers.{li}."
+        for sfx in ("", "_moe_gen"):
+            a = p + "self_attn."
+            sd[a + f"q_proj{sfx}.weight"] = _normal(g, (Hq * d, H), w_std)
+            sd[a + f"q_proj{sfx}.bias"] = _normal(g, (Hq * d,), 0.1)
+            sd[a + f"k_proj{sfx}.weight"] = _normal(g, (Hk * d, H), w_std)
+            sd[a + f"k_proj{sfx}.bias"] = _normal(g, (Hk * d,), 0.1)
+            sd[a + f"v_proj{sfx}.weight"] = _normal(g, (Hk * d, H), w_std)
+            sd[a + f"v_proj{sfx}.bias"] = _normal(g, (Hk * d,), 0.1)
+            sd[a + f"o_proj{sfx}.weight"] = _normal(g, (H, Hq * d), w_std)
+            sd[a + f"q_norm{sfx}.weight"] = 1.0 + _normal(g, (d,), 0.1)
+            sd[a + f"k_norm{sfx}.weight"] = 1.0 + _normal(g, (d,), 0.1)
+            m = p + f"mlp{sfx}."
+            sd[m + "gate_proj.weight"] = _normal(g, (I, H), w_std)
+            sd[m + "up_proj.weight"] = _normal(g, (I, H), w_std)
+            sd[m + "down_proj.weight"] = _normal(g, (H, I), w_std)
+            sd[p + f"input_layernorm{sfx}.weight"] = 1.0 + _normal(g, (H,), 0.1)
+            sd[p + f"post_attention_layernorm{sfx}.weight"] = 1.0 + _normal(g, (H,), 0.1)
+    sd["model.norm.weight"] = 1.0 + _normal(g, (H,), 0.1)
+    sd["model.norm_moe_gen.weight"] = 1.0 + _normal(g, (H,), 0.1)
+    if lm_head:
+        sd["lm_head.weight"] = _normal(g, (cfg.vocab_size, H), w_std)
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def bagel_extra_state_dict(hidden: int, patch_latent_dim: int = 64, seed: int = 1, dtype=torch.bfloat16,
+                           w_std: float = 0.05) -> Dict[str, torch.Tensor]:
+    """time_embedder / vae2llm / llm2vae parameters (bagel.py:78-82). The two frozen 2-D sincos tables
+    (latent_pos_embed, vit_pos_embed) are deterministic and are built by the code under test."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {
+        "time_embedder.mlp.0.weight": _normal(g, (hidden, 256), w_std),
+        "time_embedder.mlp.0.bias": _normal(g, (hidden,), 0.1),
+        "time_embedder.mlp.2.weight": _normal(g, (hidden, hidden), w_std),
+        "time_embedder.mlp.2.bias": _normal(g, (hidden,), 0.1),
+        "vae2llm.weight": _normal(g, (hidden, patch_latent_dim), w_std * 2),
+        "vae2llm.bias": _normal(g, (hidden,), 0.1),
+        "llm2vae.weight": _normal(g, (patch_latent_dim, hidden), w_std),
+        "llm2vae.bias": _normal(g, (patch_latent_dim,), 0.1),
+    }
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def config1_inputs(cfg: LMConfig = TINY_LM, seq: int = 512, seed: int = 0, dtype=torch.bfloat16):
+    """BASELINE.json configs[0] / SURVEY.md §8(d) cfg 1: one packed sequence of 512 rows."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn((seq, cfg.hidden_size), generator=g, dtype=torch.float32).to(dtype)
+    return {
+        "x": x,
+        "query_lens": torch.tensor([seq], dtype=torch.int32),
+        "und_position_ids": torch.arange(seq, dtype=torch.long),
+        "gen_position_ids": torch.full((seq,), 7, dtype=torch.long),
+        "query_indexes": torch.arange(seq, dtype=torch.long),
+        "text_indexes": torch.tensor([0, seq - 1], dtype=torch.long),
+        "vae_indexes": torch.arange(1, seq - 1, dtype=torch.long),
+    }

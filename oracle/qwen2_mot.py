@@ -1,0 +1,211 @@
+"""TEST INFRASTRUCTURE — CPU restatement of the packed MoT Qwen2 language model forward
+(reference: modeling/bagel/qwen2_navit.py:499-600, 757-831, 1018-1092; modeling/qwen2/modeling_qwen2.py:45-201).
+
+Pure functions over `sd`, a dict with the reference's parameter names (prefix "model." for the decoder,
+"lm_head.weight"). Dtype behaviour follows the reference under `torch.autocast(bfloat16)`: every nn.Linear
+runs with bf16 operands and returns bf16; elementwise ops follow torch type promotion. `sd` may hold bf16
+weights ("mode A", app.py:111) or fp32 weights ("mode B", eval/gen/gen_images_mp.py:159-175).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class LMConfig:
+    hidden_size: int
+    intermediate_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    vocab_size: int
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1000000.0
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+
+def linear(x, w, b=None):
+    """nn.Linear under autocast(bf16): operands cast to bf16, bf16 result."""
+    return F.linear(x.to(BF16), w.to(BF16), None if b is None else b.to(BF16))
+
+
+def rms_norm(x, w, eps):
+    """modeling_qwen2.py:54-59 — cast back to the input dtype BEFORE the weight multiply."""
+    dt = x.dtype
+    x32 = x.to(torch.float32)
+    var = x32.pow(2).mean(-1, keepdim=True)
+    x32 = x32 * torch.rsqrt(var + eps)
+    return w * x32.to(dt)
+
+
+def rope_tables(position_ids, head_dim, theta, dtype):
+    """modeling_qwen2.py:130-150 — fp32 angles, halves duplicated, then cast to the hidden-stream dtype."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    freqs = (inv_freq[None, :, None].float() @ position_ids[None, None, :].float()).transpose(1, 2)[0]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def _rot_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+def apply_rope(q, k, cos, sin):
+    """modeling_qwen2.py:162-186 with unsqueeze_dim=1 (heads)."""
+    c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+    return q * c + _rot_half(q) * s, k * c + _rot_half(k) * s
+
+
+def swiglu_mlp(x, sd, pfx):
+    """modeling_qwen2.py:200-201."""
+    g = linear(x, sd[pfx + "gate_proj.weight"])
+    u = linear(x, sd[pfx + "up_proj.weight"])
+    return linear(F.silu(g) * u, sd[pfx + "down_proj.weight"])
+
+
+def varlen_attention(q, k, v, q_lens, k_lens, causal):
+    """Semantics of flash_attn_varlen_func as the reference calls it (qwen2_navit.py:579-588): per-sample
+    softmax(q k^T / sqrt(d)) v, GQA, bottom-right aligned causal mask, fp32 math on bf16 inputs, bf16 out."""
+    out = torch.empty_like(q)
+    rep = q.shape[1] // k.shape[1]
+    scale = q.shape[-1] ** -0.5
+    qs = ks = 0
+    for lq, lk in zip(q_lens, k_lens):
+        lq, lk = int(lq), int(lk)
+        if lq:
+            qb = q[qs:qs + lq].float().transpose(0, 1)
+            kb = k[ks:ks + lk].float().transpose(0, 1).repeat_interleave(rep, dim=0)
+            vb = v[ks:ks + lk].float().transpose(0, 1).repeat_interleave(rep, dim=0)
+            s = torch.matmul(qb, kb.transpose(1, 2)) * scale
+            if causal:
+                keep = torch.ones(lq, lk, dtype=torch.bool).tril(diagonal=lk - lq)
+                s = s.masked_fill(~keep, float("-inf"))
+            out[qs:qs + lq] = torch.matmul(torch.softmax(s, dim=-1), vb).transpose(0, 1).to(q.dtype)
+        qs += lq
+        ks += lk
+    return out
+
+
+class KVCache:
+    """Mirror of NaiveCache (qwen2_navit.py:207-221): per-layer packed [sum kv, Hk, d] tensors or None."""
+
+    def __init__(self, num_layers):
+        self.key_cache = {i: None for i in range(num_layers)}
+        self.value_cache = {i: None for i in range(num_layers)}
+
+
+def _attention(x, sd, cfg: LMConfig, li: int, cos, sin, query_lens, packed_query_indexes, cache: Optional[KVCache],
+               key_values_lens, packed_key_value_indexes, update, is_causal, mode, vae_idx, text_idx):
+    """qwen2_navit.py:499-600 (PackedAttentionMoT.forward_inference)."""
+    p = f"model.layers.{li}.self_attn."
+    Hq, Hk, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    eps = cfg.rms_norm_eps
+    if mode == "und":
+        q = linear(x, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"]).view(-1, Hq, d)
+        k = linear(x, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"]).view(-1, Hk, d)
+        v = linear(x, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"]).view(-1, Hk, d)
+        q = rms_norm(q, sd[p + "q_norm.weight"], eps)
+        k = rms_norm(k, sd[p + "k_norm.weight"], eps)
+    else:
+        x = x.to(BF16)
+        n = x.shape[0]
+        q = x.new_zeros((n, Hq * d))
+        k = x.new_zeros((n, Hk * d))
+        v = x.new_zeros((n, Hk * d))
+        xt, xv = x[text_idx], x[vae_idx]
+        for dst, name in ((q, "q"), (k, "k"), (v, "v")):
+            dst[text_idx] = linear(xt, sd[p + f"{name}_proj.weight"], sd[p + f"{name}_proj.bias"])
+            dst[vae_idx] = linear(xv, sd[p + f"{name}_proj_moe_gen.weight"], sd[p + f"{name}_proj_moe_gen.bias"])
+        q, k, v = q.view(-1, Hq, d), k.view(-1, Hk, d), v.view(-1, Hk, d)
+        q = q.to(torch.float32)
+        q[text_idx] = rms_norm(q[text_idx], sd[p + "q_norm.weight"], eps)
+        q[vae_idx] = rms_norm(q[vae_idx], sd[p + "q_norm_moe_gen.weight"], eps)
+        k = k.to(torch.float32)
+        k[text_idx] = rms_norm(k[text_idx], sd[p + "k_norm.weight"], eps)
+        k[vae_idx] = rms_norm(k[vae_idx], sd[p + "k_norm_moe_gen.weight"], eps)
+
+    q, k = apply_rope(q, k, cos, sin)
+    q, k, v = q.to(BF16), k.to(BF16), v.to(BF16)
+
+    if cache is not None and cache.key_cache[li] is not None:
+        pk, pv = cache.key_cache[li], cache.value_cache[li]
+        total = int(sum(query_lens)) + int(sum(key_values_lens))
+        mk = pk.new_zeros((total, Hk, d))
+        mv = pk.new_zeros((total, Hk, d))
+        mk[packed_query_indexes] = k
+        mk[packed_key_value_indexes] = pk
+        mv[packed_query_indexes] = v
+        mv[packed_key_value_indexes] = pv
+        kv_lens = key_values_lens + query_lens
+    else:
+        mk, mv, kv_lens = k, v, query_lens
+
+    o = varlen_attention(q, mk, mv, query_lens.tolist(), kv_lens.tolist(), is_causal)
+    o = o.reshape(-1, Hq * d)
+    if mode == "und":
+        o = linear(o, sd[p + "o_proj.weight"])
+    else:
+        o[text_idx] = linear(o[text_idx], sd[p + "o_proj.weight"])
+        o[vae_idx] = linear(o[vae_idx], sd[p + "o_proj_moe_gen.weight"])
+    if update:
+        cache.key_cache[li], cache.value_cache[li] = mk, mv
+    return o
+
+
+def _layer(x, sd, cfg, li, cos, sin, mode, vae_idx, text_idx, **attn_kw):
+    """qwen2_navit.py:757-831 (Qwen2MoTDecoderLayer.forward_inference, TaylorSeer off)."""
+    p = f"model.layers.{li}."
+    eps = cfg.rms_norm_eps
+    resid = x
+    if mode == "und":
+        h = rms_norm(x, sd[p + "input_layernorm.weight"], eps)
+    else:
+        h = torch.zeros_like(x)
+        h[text_idx] = rms_norm(x[text_idx], sd[p + "input_layernorm.weight"], eps)
+        h[vae_idx] = rms_norm(x[vae_idx], sd[p + "input_layernorm_moe_gen.weight"], eps)
+    a = _attention(h, sd, cfg, li, cos, sin, mode=mode, vae_idx=vae_idx, text_idx=text_idx, **attn_kw)
+    x = resid + a
+    resid = x
+    if mode == "und":
+        h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], eps)
+        m = swiglu_mlp(h, sd, p + "mlp.")
+    else:
+        ht = rms_norm(x[text_idx], sd[p + "post_attention_layernorm.weight"], eps).to(BF16)
+        hv = rms_norm(x[vae_idx], sd[p + "post_attention_layernorm_moe_gen.weight"], eps).to(BF16)
+        m = torch.zeros_like(x).to(BF16)
+        m[text_idx] = swiglu_mlp(ht, sd, p + "mlp.")
+        m[vae_idx] = swiglu_mlp(hv, sd, p + "mlp_moe_gen.")
+    return resid + m
+
+
+def lm_forward_inference(sd: Dict[str, torch.Tensor], cfg: LMConfig, packed_query_sequence, query_lens,
+                         packed_query_position_ids, packed_query_indexes, past_key_values: Optional[KVCache] = None,
+                         key_values_lens=None, packed_key_value_indexes=None, update_past_key_values=True,
+                         is_causal=True, mode="und", packed_vae_token_indexes=None, packed_text_indexes=None):
+    """qwen2_navit.py:1018-1092 (Qwen2Model.forward_inference). Returns (hidden [N,H], cache)."""
+    x = packed_query_sequence
+    cos, sin = rope_tables(packed_query_position_ids, cfg.head_dim, cfg.rope_theta, x.dtype)
+    for li in range(cfg.num_hidden_layers):
+        x = _layer(x, sd, cfg, li, cos, sin, mode, packed_vae_token_indexes, packed_text_indexes,
+                   query_lens=query_lens, packed_query_indexes=packed_query_indexes, cache=past_key_values,
+                   key_values_lens=key_values_lens, packed_key_value_indexes=packed_key_value_indexes,
+                   update=update_past_key_values, is_causal=is_causal)
+    eps = cfg.rms_norm_eps
+    if mode == "und":
+        x = rms_norm(x, sd["model.norm.weight"], eps)
+    else:
+        y = torch.zeros_like(x)
+        y[packed_text_indexes] = rms_norm(x[packed_text_indexes], sd["model.norm.weight"], eps)
+        y[packed_vae_token_indexes] = rms_norm(x[packed_vae_token_indexes], sd["model.norm_moe_gen.weight"], eps)
+        x = y
+    return x, past_key_values
