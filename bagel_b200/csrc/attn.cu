@@ -1,0 +1,378 @@
+// Packed variable-length flash attention forward for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Drop-in for the reference's only native seam, flash_attn_varlen_func (FA2, mma.sync) as called at
+// modeling/bagel/qwen2_navit.py:361-370, 579-588 and modeling/bagel/siglip_navit.py:232-241:
+//   out[Sq,Hq,D] = softmax(q k^T * scale [+ bottom-right causal mask]) v   per packed sample, GQA by Hq % Hk == 0,
+//   bf16 in / fp32 softmax + accumulation / bf16 out.
+//
+// One CTA owns TWO 128-row query tiles of one (sample, head) and sweeps the keys in blocks of 128:
+//   warps 0-3     softmax group of tile 0 (thread = row): tcgen05.ld S -> online softmax -> P (bf16) back into
+//   warps 4-7     softmax group of tile 1                  the S columns of TMEM; rescales O in TMEM when the
+//                                                          running max grows; final O / l -> global
+//   warp 8        TMA producer: Q tiles once, then K_j / V_j blocks through a kStages smem ring
+//   warp 9        MMA issuer (one lane): S_t = Q_t K_j^T  (SS, both K-major)  and  O_t += P_t V_j (TS: A = P in TMEM,
+//                 B = V MN-major) — the tensor pipe runs tile 0 while tile 1 is in softmax and vice versa
+// TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D); P_t aliases S_t columns [0,64).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace bagel {
+
+constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax tile 0 | softmax tile 1 | {TMA, MMA, 2 idle}
+constexpr int kBlockM = 128;  // rows per query tile (2 tiles per CTA)
+constexpr int kBlockN = 128;  // keys per block
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  long long ld_out;  // elements between consecutive rows of out (= Hq*D for packed layout)
+  const int* cu_q;   // [B+1]
+  const int* cu_k;   // [B+1]
+  int Hq, Hk;
+  int causal;
+  float scale_log2;  // softmax_scale * log2(e)
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
+  static constexpr int kStages = (D == 128) ? 4 : 6;
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kTileBytes = Cfg::kTileBytes;
+  constexpr int kAtoms = D / 64;               // 64-column (128 B) swizzle atoms per row
+  constexpr int kAtomBytes = kBlockM * 128;    // one [128 rows x 64 cols] box
+
+  const int b = blockIdx.z;
+  const int h = blockIdx.y;
+  const int q_beg = p.cu_q[b], Lq = p.cu_q[b + 1] - q_beg;
+  const int k_beg = p.cu_k[b], Lk = p.cu_k[b + 1] - k_beg;
+  const int q0 = blockIdx.x * 2 * kBlockM;  // first query row (within the sample) of this CTA
+  if (q0 >= Lq) return;                     // whole CTA idle (grid is sized by max_seqlen_q)
+  const bool tile1_active = (q0 + kBlockM) < Lq;
+  const int hk = h / (p.Hq / p.Hk);
+  const int shift = Lk - Lq;  // bottom-right aligned causal: key kv visible to query qi iff kv <= qi + shift
+
+  // number of key blocks this CTA sweeps
+  int kv_end = Lk;
+  if (p.causal) {
+    const int q_hi = min(Lq, q0 + 2 * kBlockM) - 1;
+    kv_end = max(0, min(Lk, q_hi + shift + 1));
+  }
+  const int nblk = (kv_end + kBlockN - 1) / kBlockN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                      // 2 tiles
+  uint8_t* smem_kv = smem + 2 * kTileBytes;    // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kStages * kTileBytes);
+  uint64_t* q_bar = bars;                  // [1]
+  uint64_t* kv_full = bars + 1;            // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;  // [kStages]
+  uint64_t* s_bar = kv_empty + kStages;    // [2]  MMA -> softmax: S_t(j) ready
+  uint64_t* p_bar = s_bar + 2;             // [2]  softmax -> MMA: P_t(j) written (and O_t rescaled)
+  uint64_t* o_bar = p_bar + 2;             // [2]  MMA -> softmax: final O_t ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_bar, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_bar[t], 1);
+      mbar_init(&p_bar[t], 4);
+      mbar_init(&o_bar[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S[2] = {tmem_base + 0, tmem_base + 128};
+  const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    if (lane == 0 && nblk > 0) {
+      const int ntile = tile1_active ? 2 : 1;
+      mbar_expect_tx(q_bar, ntile * kTileBytes);
+      for (int t = 0; t < ntile; ++t)
+        for (int a = 0; a < kAtoms; ++a)
+          tma_load_2d(smem_q + t * kTileBytes + a * kAtomBytes, &tmQ, q_bar, h * D + a * 64,
+                      q_beg + q0 + t * kBlockM, kEvictFirst);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_expect_tx(&kv_full[stage], kTileBytes);
+          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+          for (int a = 0; a < kAtoms; ++a)
+            tma_load_2d(smem_kv + stage * kTileBytes + a * kAtomBytes, tm, &kv_full[stage], hk * D + a * 64,
+                        k_beg + j * kBlockN, kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0 && nblk > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S[128,128] = Q[128,D] K[128,D]^T
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, D, 0, 1);        // O[128,D] += P[128,128] V[128,D]
+      const int ntile = tile1_active ? 2 : 1;
+      int stage = 0;
+      uint32_t phase = 0;
+
+      auto issue_qk = [&](int t, int kstage) {
+        // K-major operands: D columns = kAtoms atoms of 64; 4 UMMA_K=16 steps per atom (+32 B each)
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a) {
+          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + t * kTileBytes + a * kAtomBytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_kv + kstage * kTileBytes + a * kAtomBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_S[t], a_desc + 2 * k, b_desc + 2 * k, idesc_qk, (a | k) != 0);
+        }
+        umma_commit(&s_bar[t]);
+      };
+      auto issue_pv = [&](int t, int vstage, bool accumulate) {
+        // A = P_t from TMEM (bf16 pairs: 16 keys = 8 columns per UMMA_K step);
+        // B = V block, MN-major: 64-col halves LBO = kAtomBytes apart, 8-key groups 1024 B apart, 16 keys = 2048 B
+        const uint32_t vbase = smem_u32(smem_kv + vstage * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBlockN / 16; ++k) {
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(vbase + k * 2048, kAtomBytes);
+          umma_ts(tmem_O[t], tmem_S[t] + k * 8, b_desc, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_bar, 0);
+      // block 0 scores for both tiles
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      for (int t = 0; t < ntile; ++t) issue_qk(t, stage);
+      umma_commit(&kv_empty[stage]);  // K_0 slot free once both S(0) are done
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+
+      for (int j = 0; j < nblk; ++j) {
+        const int vstage = stage;
+        mbar_wait(&kv_full[vstage], phase);  // V_j
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        const int kstage = stage;
+        const bool has_next = (j + 1) < nblk;
+        if (has_next) {
+          mbar_wait(&kv_full[kstage], phase);  // K_{j+1}
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_fence_after();
+        for (int t = 0; t < ntile; ++t) {
+          mbar_wait(&p_bar[t], j & 1);  // P_t(j) in TMEM, O_t rescaled
+          tc_fence_after();
+          issue_pv(t, vstage, j > 0);
+          if (!has_next) umma_commit(&o_bar[t]);
+          // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
+          if (has_next) issue_qk(t, kstage);
+        }
+        umma_commit(&kv_empty[vstage]);
+        if (has_next) umma_commit(&kv_empty[kstage]);
+      }
+    }
+  } else if (warp < 8) {
+    // =========================== softmax / correction / epilogue ===========================
+    const int t = warp >> 2;        // which query tile this warp group serves
+    const int quarter = warp & 3;   // TMEM lane quarter accessible to this warp
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + t * kBlockM + row;  // query index within the sample
+    const bool active = (t == 0) || tile1_active;
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    const uint32_t tS = tmem_S[t] + lane_off;
+    const uint32_t tO = tmem_O[t] + lane_off;
+
+    if (active) {
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&s_bar[t], j & 1);
+        tc_fence_after();
+        // registers written by tcgen05.ld may only be read after wait::ld
+        uint32_t sr[kBlockN];
+#pragma unroll
+        for (int c = 0; c < kBlockN / 32; ++c)
+          tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
+        tmem_ld_wait();
+        float* s = reinterpret_cast<float*>(sr);
+
+        const int kv0 = j * kBlockN;
+        const int tile_q_lo = q0 + t * kBlockM;
+        const bool need_mask = (kv0 + kBlockN > Lk) || (p.causal && (kv0 + kBlockN - 1 > tile_q_lo + shift));
+        if (need_mask) {
+          const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
+#pragma unroll
+          for (int i = 0; i < kBlockN; ++i)
+            if (kv0 + i > lim) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < kBlockN; ++i) mx = fmaxf(mx, s[i]);
+        const float m_new = fmaxf(m, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2((m - m_use) * p.scale_log2);  // m = -inf -> 0
+        const bool grow = (j > 0) && (m_new > m);
+        if (__any_sync(0xffffffffu, grow)) {
+          // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order.
+          const float a = grow ? alpha : 1.f;
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tO + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * a);
+            tmem_st_x32(tO + c * 32, v);
+          }
+        }
+        const float neg_ms = -m_use * p.scale_log2;
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < kBlockN / 64; ++c) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2(fmaf(s[c * 64 + 2 * i], p.scale_log2, neg_ms));
+            const float p1 = ex2(fmaf(s[c * 64 + 2 * i + 1], p.scale_log2, neg_ms));
+            rs += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x32(tS + c * 32, pk);
+        }
+        l = l * alpha + rs;
+        m = m_new;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_bar[t]);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> global ----
+      if (nblk > 0) {
+        mbar_wait(&o_bar[t], 0);
+        tc_fence_after();
+      }
+      const float inv_l = (l > 0.f) ? (1.f / l) : 0.f;
+      const bool row_ok = qi < Lq;
+      __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        if (nblk > 0) {
+          tmem_ld_x32(tO + c * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2 * e]) * inv_l, __uint_as_float(v[q4 * 8 + 2 * e + 1]) * inv_l);
+            dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
+                       int B, int max_seqlen_q, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  auto kern = attn_varlen_kernel<D>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid((max_seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM), p.Hq, B);
+  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bagel
+
+using namespace bagel;
+
+extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,
+                                     const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
+                                     int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,
+                                     float softmax_scale, long long ld_q, long long ld_k, long long ld_v,
+                                     long long ld_out, void* stream) {
+  (void)max_seqlen_k;
+  if (head_dim != 64 && head_dim != 128)
+    return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: head_dim must be 64 or 128 (got %d)", head_dim);
+  if (num_heads_k <= 0 || num_heads_q % num_heads_k)
+    return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: num_heads_q %% num_heads_k != 0");
+  if (batch <= 0 || total_q < 0 || total_k < 0) return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: bad sizes");
+  if ((ld_q % 8) || (ld_k % 8) || (ld_v % 8) || (ld_out % 8) || (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15))
+    return set_error(BAGEL_ERR_ALIGN, "bagel_attn_varlen_fwd: row strides %% 8 and 16-byte aligned pointers required");
+  if (int rc = require_sm100()) return rc;
+  if (total_q == 0 || max_seqlen_q <= 0) return 0;
+
+  CUtensorMap tmQ, tmK, tmV;
+  if (int rc = make_tmap_2d_bf16(&tmQ, q, (uint64_t)num_heads_q * head_dim, (uint64_t)total_q, (uint64_t)ld_q, 64, kBlockM)) return rc;
+  const uint64_t rows_k = total_k > 0 ? (uint64_t)total_k : 1;
+  if (int rc = make_tmap_2d_bf16(&tmK, k, (uint64_t)num_heads_k * head_dim, rows_k, (uint64_t)ld_k, 64, kBlockN)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmV, v, (uint64_t)num_heads_k * head_dim, rows_k, (uint64_t)ld_v, 64, kBlockN)) return rc;
+
+  AttnParams p{};
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  p.cu_q = cu_seqlens_q;
+  p.cu_k = cu_seqlens_k;
+  p.Hq = num_heads_q;
+  p.Hk = num_heads_k;
+  p.causal = causal;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (head_dim == 128) return launch_attn<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  return launch_attn<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+}

@@ -1,0 +1,468 @@
+// HBM-bound glue kernels of the MoT forward path (everything that is not a GEMM or attention).
+// Each replaces a chain of ATen elementwise / index launches in the reference and keeps the reference's bf16
+// rounding points ("mode A": bf16 weights under autocast). All are simple streaming kernels:
+// 16-byte vector loads/stores, one warp per row (or per head), fp32 math, warp-shuffle reductions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace bagel {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm with per-row expert routing (Qwen2RMSNorm, modeling/qwen2/modeling_qwen2.py:54-59; MoT routing
+// of input/post-attention/final norms, modeling/bagel/qwen2_navit.py:781-787, 808-815, 1075-1082).
+//   y = bf16( w_e * bf16( x * rsqrt(mean(x^2) + eps) ) ),  e = expert[row] (0: und weights, 1: gen weights)
+// One warp per row, the row stays in registers between the reduction and the scale (single HBM pass).
+// ---------------------------------------------------------------------------------------------
+template <int VPL>  // 16-byte vectors per lane
+__global__ void __launch_bounds__(128)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w0,
+               const __nv_bfloat16* __restrict__ w1, const uint8_t* __restrict__ expert,
+               __nv_bfloat16* __restrict__ y, long long ldy, int N, int H, float eps) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int nvec = H >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4 v[VPL];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_lo(u[e]), b = bf16_hi(u[e]);
+        ss += a * a + b * b;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / (float)H + eps);
+  const __nv_bfloat16* w = (expert != nullptr && w1 != nullptr && expert[row]) ? w1 : w0;
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const uint4 wv = wr[idx];
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_round(bf16_lo(u[e]) * r), b = bf16_round(bf16_hi(u[e]) * r);
+        o[e] = pack_bf16x2(bf16_lo(ww[e]) * a, bf16_hi(ww[e]) * b);
+      }
+      yr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE tables (Qwen2RotaryEmbedding.forward, modeling_qwen2.py:130-150): angle = pos * inv_freq in fp32,
+// cos/sin optionally rounded to bf16 (the reference casts them to the hidden-stream dtype). Halves are
+// duplicated in the reference; we store D/2 columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(const long long* __restrict__ pos, const float* __restrict__ inv_freq,
+                                  float* __restrict__ cos_t, float* __restrict__ sin_t, int N, int half,
+                                  int round_bf16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * half) return;
+  const int r = (int)(i / half), c = (int)(i % half);
+  const float ang = __fmul_rn((float)pos[r], inv_freq[c]);
+  float cs = cosf(ang), sn = sinf(ang);
+  if (round_bf16) { cs = bf16_round(cs); sn = bf16_round(sn); }
+  cos_t[i] = cs;
+  sin_t[i] = sn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-head q/k RMSNorm + RoPE + bf16 cast + K/V placement into the merged KV buffer
+// (PackedAttentionMoT.forward_inference, qwen2_navit.py:518-519 / 542-557 and the KV merge :559-574).
+//   qkv   [N, (Hq+2Hk)*D]  bf16 output of the fused QKV projection (bias included)
+//   q_out [N, Hq*D]; k_out/v_out [rows, Hk*D] written at row kv_rows[r] (the reference's packed_query_indexes)
+// fp32_flow = 1 reproduces mode="gen" (fp32 norm + RoPE, one final bf16 cast); 0 reproduces mode="und"
+// (every op rounds to bf16). One warp per (row, head).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, const __nv_bfloat16* __restrict__ qw0,
+                    const __nv_bfloat16* __restrict__ kw0, const __nv_bfloat16* __restrict__ qw1,
+                    const __nv_bfloat16* __restrict__ kw1, const uint8_t* __restrict__ expert,
+                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                    __nv_bfloat16* __restrict__ q_out, long long ld_q, __nv_bfloat16* __restrict__ k_out,
+                    __nv_bfloat16* __restrict__ v_out, long long ld_kv, const int* __restrict__ kv_rows, int N,
+                    int Hq, int Hk, float eps, int fp32_flow) {
+  constexpr int E = D / 64;  // elements per lane in each half
+  constexpr int HALF = D / 2;
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nheads = Hq + 2 * Hk;
+  const bool gen = (expert != nullptr && qw1 != nullptr && expert[row]);
+  const long long dst_row = kv_rows ? (long long)kv_rows[row] : (long long)row;
+  const __nv_bfloat16* src_row = qkv + (long long)row * ld_qkv;
+
+  float cs[E], sn[E];
+#pragma unroll
+  for (int t = 0; t < E; ++t) {
+    cs[t] = cos_t[(long long)row * HALF + lane * E + t];
+    sn[t] = sin_t[(long long)row * HALF + lane * E + t];
+  }
+
+  for (int hh = warp; hh < nheads; hh += 4) {
+    const __nv_bfloat16* src = src_row + hh * D;
+    float a[E], b[E];  // first-half / second-half elements owned by this lane
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      a[t] = __bfloat162float(src[lane * E + t]);
+      b[t] = __bfloat162float(src[HALF + lane * E + t]);
+    }
+    __nv_bfloat16* dst;
+    if (hh < Hq) dst = q_out + (long long)row * ld_q + hh * D;
+    else if (hh < Hq + Hk) dst = k_out + dst_row * ld_kv + (hh - Hq) * D;
+    else dst = v_out + dst_row * ld_kv + (hh - Hq - Hk) * D;
+
+    if (hh >= Hq + Hk) {  // V: plain copy
+#pragma unroll
+      for (int t = 0; t < E; ++t) {
+        dst[lane * E + t] = __float2bfloat16_rn(a[t]);
+        dst[HALF + lane * E + t] = __float2bfloat16_rn(b[t]);
+      }
+      continue;
+    }
+    const __nv_bfloat16* w = (hh < Hq) ? (gen ? qw1 : qw0) : (gen ? kw1 : kw0);
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < E; ++t) ss += a[t] * a[t] + b[t] * b[t];
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      const float wa = __bfloat162float(w[lane * E + t]);
+      const float wb = __bfloat162float(w[HALF + lane * E + t]);
+      float ya, yb, oa, ob;
+      if (fp32_flow) {
+        ya = __fmul_rn(wa, __fmul_rn(a[t], r));
+        yb = __fmul_rn(wb, __fmul_rn(b[t], r));
+        // q*cos + rotate_half(q)*sin, each product rounded separately (torch does not fuse)
+        oa = __fadd_rn(__fmul_rn(ya, cs[t]), __fmul_rn(-yb, sn[t]));
+        ob = __fadd_rn(__fmul_rn(yb, cs[t]), __fmul_rn(ya, sn[t]));
+      } else {
+        ya = bf16_round(wa * bf16_round(a[t] * r));
+        yb = bf16_round(wb * bf16_round(b[t] * r));
+        oa = bf16_round(ya * cs[t]) + bf16_round(-yb * sn[t]);
+        ob = bf16_round(yb * cs[t]) + bf16_round(ya * sn[t]);
+      }
+      dst[lane * E + t] = __float2bfloat16_rn(oa);
+      dst[HALF + lane * E + t] = __float2bfloat16_rn(ob);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row gather / scatter: dst[dst_rows[i] or i] = src[src_rows[i] or i]   (token embedding lookup bagel.py:277,796,
+// modality gathers qwen2_navit.py:526-548, KV-cache placement :565-569). One warp per row, 16-byte vectors.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+copy_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ src_rows,
+                 __nv_bfloat16* __restrict__ dst, long long ldd, const int* __restrict__ dst_rows, int M, int H) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const long long sr = src_rows ? src_rows[i] : i;
+  const long long dr = dst_rows ? dst_rows[i] : i;
+  const uint4* s = reinterpret_cast<const uint4*>(src + sr * lds);
+  uint4* d = reinterpret_cast<uint4*>(dst + dr * ldd);
+  for (int v = lane; v < (H >> 3); v += 32) d[v] = s[v];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Latent-in tail (bagel.py:801-806): seq[dst_rows[i]] = bf16( bf16(proj[i] + t_emb) + pos_table[pos_ids[i]] )
+// where proj = vae2llm(x_t) (GEMM), t_emb = TimestepEmbedder(t) (one row, identical for every latent token).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+latent_embed_add_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, const __nv_bfloat16* __restrict__ t_emb,
+                        const __nv_bfloat16* __restrict__ pos_table, long long ldt,
+                        const long long* __restrict__ pos_ids, __nv_bfloat16* __restrict__ seq, long long lds,
+                        const int* __restrict__ dst_rows, int M, int H) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const uint4* pr = reinterpret_cast<const uint4*>(proj + (long long)i * ldp);
+  const uint4* te = reinterpret_cast<const uint4*>(t_emb);
+  const uint4* pt = reinterpret_cast<const uint4*>(pos_table + pos_ids[i] * ldt);
+  uint4* d = reinterpret_cast<uint4*>(seq + (long long)(dst_rows ? dst_rows[i] : i) * lds);
+  for (int v = lane; v < (H >> 3); v += 32) {
+    const uint4 a = pr[v], b = te[v], c = pt[v];
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {c.x, c.y, c.z, c.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = bf16_round(bf16_lo(ua[e]) + bf16_lo(ub[e])) + bf16_lo(uc[e]);
+      const float hi = bf16_round(bf16_hi(ua[e]) + bf16_hi(ub[e])) + bf16_hi(uc[e]);
+      o[e] = pack_bf16x2(lo, hi);
+    }
+    d[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classifier-free guidance + renorm + Euler step (bagel.py:873-907 and :746), all bf16 rounding points kept:
+//   u = vT + sT (v - vT);  w = (sI > 1) ? vI + sI (u - vI) : u;
+//   scale = clamp(|v| / (|w| + 1e-8), renorm_min, 1)  over the whole batch ("global", type 0) or per token
+//   ("channel", type 1);  "text_channel" (type 2) renormalises u per token against v before the image CFG.
+//   x <- x - bf16(bf16(w * scale) * dt)            x fp32 [M, C]
+// Pass 1 (global only) accumulates sum v^2 and sum w^2 into norms[0..1]; pass 2 applies.
+// v, vT, vI are rows of the llm2vae output selected by `rows` (the latent rows of the packed sequence).
+// ---------------------------------------------------------------------------------------------
+struct CfgArgs {
+  const __nv_bfloat16 *v, *vT, *vI;
+  long long ldv;
+  const int* rows;
+  float* x;
+  float* norms;  // [2] fp32, zeroed by the caller before pass 1
+  int M, C;
+  float sT, sI, renorm_min, dt;
+  int renorm_type;
+};
+
+__device__ __forceinline__ void cfg_combine(const CfgArgs& a, float v, float vT, float vI, float& u, float& w) {
+  // bf16 tensor arithmetic with python-float scalars: every op rounds to bf16
+  u = bf16_round(vT + bf16_round(a.sT * bf16_round(v - vT)));
+  w = (a.sI > 1.0f) ? bf16_round(vI + bf16_round(a.sI * bf16_round(u - vI))) : u;
+}
+
+__global__ void __launch_bounds__(256) cfg_norm_kernel(const CfgArgs a) {
+  float sv = 0.f, sw = 0.f;
+  const long long total = (long long)a.M * a.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / a.C), c = (int)(i % a.C);
+    const long long src = (long long)(a.rows ? a.rows[r] : r) * a.ldv + c;
+    const float v = __bfloat162float(a.v[src]);
+    const float vT = __bfloat162float(a.vT[src]);
+    const float vI = a.vI ? __bfloat162float(a.vI[src]) : 0.f;
+    float u, w;
+    cfg_combine(a, v, vT, vI, u, w);
+    sv += v * v;
+    sw += w * w;
+  }
+  sv = warp_sum(sv);
+  sw = warp_sum(sw);
+  __shared__ float sh[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = sv; sh[1][warp] = sw; }
+  __syncthreads();
+  if (warp == 0) {
+    sv = lane < 8 ? sh[0][lane] : 0.f;
+    sw = lane < 8 ? sh[1][lane] : 0.f;
+    sv = warp_sum(sv);
+    sw = warp_sum(sw);
+    if (lane == 0) { atomicAdd(&a.norms[0], sv); atomicAdd(&a.norms[1], sw); }
+  }
+}
+
+// one warp per latent token (C = 64 channels -> 2 per lane)
+__global__ void __launch_bounds__(128) cfg_apply_kernel(const CfgArgs a, int use_cfg) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= a.M) return;
+  const long long src = (long long)(a.rows ? a.rows[r] : r) * a.ldv;
+  float gscale = 1.f;
+  if (use_cfg && a.renorm_type == 0) {
+    const float nv = bf16_round(sqrtf(a.norms[0])), nw = bf16_round(sqrtf(a.norms[1]));
+    gscale = fminf(fmaxf(bf16_round(nv / bf16_round(nw + 1e-8f)), a.renorm_min), 1.0f);
+  }
+  float vv[4], ww[4];
+  int cnt = 0;
+  float sv = 0.f, sw = 0.f;
+  for (int c = lane; c < a.C; c += 32, ++cnt) {
+    const float v = __bfloat162float(a.v[src + c]);
+    float w = v;
+    if (use_cfg) {
+      const float vT = __bfloat162float(a.vT[src + c]);
+      const float vI = a.vI ? __bfloat162float(a.vI[src + c]) : 0.f;
+      if (a.renorm_type == 2) {
+        w = bf16_round(vT + bf16_round(a.sT * bf16_round(v - vT)));  // u; image CFG applied after renorm
+      } else {
+        float u;
+        cfg_combine(a, v, vT, vI, u, w);
+      }
+    }
+    vv[cnt] = v;
+    ww[cnt] = w;
+    sv += v * v;
+    sw += w * w;
+  }
+  float scale = gscale;
+  if (use_cfg && a.renorm_type != 0) {
+    sv = warp_sum(sv);
+    sw = warp_sum(sw);
+    const float nv = bf16_round(sqrtf(sv)), nw = bf16_round(sqrtf(sw));
+    scale = fminf(fmaxf(bf16_round(nv / bf16_round(nw + 1e-8f)), a.renorm_min), 1.0f);
+  }
+  cnt = 0;
+  for (int c = lane; c < a.C; c += 32, ++cnt) {
+    float w = ww[cnt];
+    if (use_cfg) {
+      w = bf16_round(w * scale);
+      if (a.renorm_type == 2 && a.sI > 1.0f) {
+        const float vI = __bfloat162float(a.vI[src + c]);
+        w = bf16_round(vI + bf16_round(a.sI * bf16_round(w - vI)));
+      }
+    }
+    float* xp = a.x + (long long)r * a.C + c;
+    *xp = *xp - bf16_round(w * a.dt);
+  }
+}
+
+// x fp32 [M, C] -> bf16 (the autocast cast in front of vae2llm)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    *reinterpret_cast<uint32_t*>(y + i) = pack_bf16x2(x[i], x[i + 1]);
+  } else if (i < n) {
+    y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+}  // namespace bagel
+
+using namespace bagel;
+
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+extern "C" int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, const void* w1, const uint8_t* expert,
+                                  void* y, long long ldy, int N, int H, float eps, void* stream) {
+  if (N <= 0) return 0;
+  if ((H % 8) || (ldx % 8) || (ldy % 8)) return set_error(BAGEL_ERR_ALIGN, "bagel_rmsnorm_bf16: H, ldx, ldy must be multiples of 8");
+  const int nvec = H / 8;
+  const int vpl = (nvec + 31) / 32;
+  dim3 grid((N + 3) / 4), block(128);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto W0 = static_cast<const __nv_bfloat16*>(w0);
+  auto W1 = static_cast<const __nv_bfloat16*>(w1);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+#define RMS_CASE(V) rmsnorm_kernel<V><<<grid, block, 0, s>>>(X, ldx, W0, W1, expert, Y, ldy, N, H, eps)
+  if (vpl <= 1) RMS_CASE(1);
+  else if (vpl <= 2) RMS_CASE(2);
+  else if (vpl <= 4) RMS_CASE(4);
+  else if (vpl <= 8) RMS_CASE(8);
+  else if (vpl <= 14) RMS_CASE(14);
+  else if (vpl <= 32) RMS_CASE(32);
+  else return set_error(BAGEL_ERR_SHAPE, "bagel_rmsnorm_bf16: H=%d too large (max 8192)", H);
+#undef RMS_CASE
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_rope_table(const long long* pos, const float* inv_freq, float* cos_t, float* sin_t, int N,
+                                int half, int round_bf16, void* stream) {
+  if (N <= 0) return 0;
+  const long long total = (long long)N * half;
+  rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pos, inv_freq, cos_t, sin_t, N, half, round_bf16);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void* q_w0, const void* k_w0,
+                                  const void* q_w1, const void* k_w1, const uint8_t* expert, const float* cos_t,
+                                  const float* sin_t, void* q_out, long long ld_q, void* k_out, void* v_out,
+                                  long long ld_kv, const int* kv_rows, int N, int Hq, int Hk, int D, float eps,
+                                  int fp32_flow, void* stream) {
+  if (N <= 0) return 0;
+  if (D != 64 && D != 128) return set_error(BAGEL_ERR_SHAPE, "bagel_qk_norm_rope: head_dim must be 64 or 128");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define QK_ARGS                                                                                                   \
+  static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(q_w0),                        \
+      static_cast<const __nv_bfloat16*>(k_w0), static_cast<const __nv_bfloat16*>(q_w1),                           \
+      static_cast<const __nv_bfloat16*>(k_w1), expert, cos_t, sin_t, static_cast<__nv_bfloat16*>(q_out), ld_q,    \
+      static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), ld_kv, kv_rows, N, Hq, Hk, eps,     \
+      fp32_flow
+  if (D == 128) qk_norm_rope_kernel<128><<<N, 128, 0, s>>>(QK_ARGS);
+  else qk_norm_rope_kernel<64><<<N, 128, 0, s>>>(QK_ARGS);
+#undef QK_ARGS
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_copy_rows_bf16(const void* src, long long lds, const int* src_rows, void* dst, long long ldd,
+                                    const int* dst_rows, int M, int H, void* stream) {
+  if (M <= 0) return 0;
+  if ((H % 8) || (lds % 8) || (ldd % 8)) return set_error(BAGEL_ERR_ALIGN, "bagel_copy_rows_bf16: H, lds, ldd %% 8");
+  copy_rows_kernel<<<(M + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, src_rows, static_cast<__nv_bfloat16*>(dst), ldd, dst_rows, M, H);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_latent_embed_add(const void* proj, long long ldp, const void* t_emb, const void* pos_table,
+                                      long long ldt, const long long* pos_ids, void* seq, long long lds,
+                                      const int* dst_rows, int M, int H, void* stream) {
+  if (M <= 0) return 0;
+  if ((H % 8) || (ldp % 8) || (ldt % 8) || (lds % 8)) return set_error(BAGEL_ERR_ALIGN, "bagel_latent_embed_add: alignment");
+  latent_embed_add_kernel<<<(M + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(proj), ldp, static_cast<const __nv_bfloat16*>(t_emb),
+      static_cast<const __nv_bfloat16*>(pos_table), ldt, pos_ids, static_cast<__nv_bfloat16*>(seq), lds, dst_rows, M, H);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_cfg_euler_step(const void* v, const void* v_text, const void* v_img, long long ldv,
+                                    const int* rows, float* x, float* norms_ws, int M, int C, float cfg_text_scale,
+                                    float cfg_img_scale, float renorm_min, int renorm_type, float dt, void* stream) {
+  if (M <= 0) return 0;
+  if (C > 128) return set_error(BAGEL_ERR_SHAPE, "bagel_cfg_euler_step: C must be <= 128");
+  if (renorm_type < 0 || renorm_type > 2) return set_error(BAGEL_ERR_ARG, "bagel_cfg_euler_step: renorm_type in {0,1,2}");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CfgArgs a{};
+  a.v = static_cast<const __nv_bfloat16*>(v);
+  a.vT = static_cast<const __nv_bfloat16*>(v_text);
+  a.vI = static_cast<const __nv_bfloat16*>(v_img);
+  a.ldv = ldv; a.rows = rows; a.x = x; a.norms = norms_ws; a.M = M; a.C = C;
+  a.sT = cfg_text_scale; a.sI = cfg_img_scale; a.renorm_min = renorm_min; a.dt = dt; a.renorm_type = renorm_type;
+  const int use_cfg = (cfg_text_scale > 1.0f && v_text != nullptr) ? 1 : 0;
+  if (use_cfg && a.sI > 1.0f && a.vI == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_cfg_euler_step: cfg_img_scale > 1 needs v_img");
+  if (use_cfg && renorm_type == 0) {
+    if (norms_ws == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_cfg_euler_step: global renorm needs norms_ws[2]");
+    BAGEL_CUDA_CHECK(cudaMemsetAsync(norms_ws, 0, 2 * sizeof(float), s));
+    const long long total = (long long)M * C;
+    int blocks = (int)((total + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    cfg_norm_kernel<<<blocks, 256, 0, s>>>(a);
+    COUNT_LAUNCH();
+  }
+  cfg_apply_kernel<<<(M + 3) / 4, 128, 0, s>>>(a, use_cfg);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+  if (n <= 0) return 0;
+  cast_f32_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

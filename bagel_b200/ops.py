@@ -68,3 +68,105 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                                      M, N, K, _ptr(bias), _ptr(resid), ldr, _ptr(row_map), epilogue, _stream())
     _cabi.check(rc, "bagel_gemm_bf16")
     return out
+
+
+def _i32(x: int) -> int:
+    return int(x)
+
+
+def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,
+                cu_seqlens_k: torch.Tensor, max_seqlen_q: int, max_seqlen_k: int, causal: bool = False,
+                softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """flash_attn_varlen_func contract (qwen2_navit.py:579-588): q [Sq,Hq,D], k/v [Sk,Hk,D] bf16."""
+    _req(q, torch.bfloat16, "q"); _req(k, torch.bfloat16, "k"); _req(v, torch.bfloat16, "v")
+    _req(cu_seqlens_q, torch.int32, "cu_seqlens_q"); _req(cu_seqlens_k, torch.int32, "cu_seqlens_k")
+    Sq, Hq, D = q.shape
+    Sk, Hk, _ = k.shape
+    assert q.stride(1) == D and k.stride(1) == D and v.stride(1) == D, "heads must be contiguous"
+    if out is None:
+        out = torch.empty((Sq, Hq, D), dtype=torch.bfloat16, device=q.device)
+    if softmax_scale is None:
+        softmax_scale = D ** -0.5
+    B = cu_seqlens_q.numel() - 1
+    rc = _cabi.lib().bagel_attn_varlen_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(cu_seqlens_q), _ptr(cu_seqlens_k),
+                                           Sq, Sk, B, Hq, Hk, D, int(max_seqlen_q), int(max_seqlen_k), int(bool(causal)),
+                                           float(softmax_scale), q.stride(0), k.stride(0), v.stride(0), out.stride(0),
+                                           _stream())
+    _cabi.check(rc, "bagel_attn_varlen_fwd")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w0: torch.Tensor, w1: Optional[torch.Tensor] = None,
+            expert: Optional[torch.Tensor] = None, eps: float = 1e-6, out: Optional[torch.Tensor] = None):
+    _req(x, torch.bfloat16, "x"); _req(w0, torch.bfloat16, "w0")
+    N, H = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    if expert is not None:
+        _req(expert, torch.uint8, "expert")
+    rc = _cabi.lib().bagel_rmsnorm_bf16(_ptr(x), x.stride(0), _ptr(w0), _ptr(w1), _ptr(expert), _ptr(out), out.stride(0),
+                                        N, H, float(eps), _stream())
+    _cabi.check(rc, "bagel_rmsnorm_bf16")
+    return out
+
+
+def rope_table(pos: torch.Tensor, inv_freq: torch.Tensor, round_bf16: bool = True):
+    _req(pos, torch.int64, "pos"); _req(inv_freq, torch.float32, "inv_freq")
+    N, half = pos.numel(), inv_freq.numel()
+    cos = torch.empty((N, half), dtype=torch.float32, device=pos.device)
+    sin = torch.empty_like(cos)
+    rc = _cabi.lib().bagel_rope_table(_ptr(pos), _ptr(inv_freq), _ptr(cos), _ptr(sin), N, half, int(round_bf16), _stream())
+    _cabi.check(rc, "bagel_rope_table")
+    return cos, sin
+
+
+def qk_norm_rope(qkv, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D,
+                 eps: float, fp32_flow: bool):
+    _req(qkv, torch.bfloat16, "qkv")
+    N = qkv.shape[0]
+    rc = _cabi.lib().bagel_qk_norm_rope(_ptr(qkv), qkv.stride(0), _ptr(q_w0), _ptr(k_w0), _ptr(q_w1), _ptr(k_w1),
+                                        _ptr(expert), _ptr(cos), _ptr(sin), _ptr(q_out), q_out.stride(0), _ptr(k_out),
+                                        _ptr(v_out), k_out.stride(0), _ptr(kv_rows), N, Hq, Hk, D, float(eps),
+                                        int(fp32_flow), _stream())
+    _cabi.check(rc, "bagel_qk_norm_rope")
+
+
+def copy_rows(src, dst, src_rows=None, dst_rows=None, M: Optional[int] = None):
+    _req(src, torch.bfloat16, "src"); _req(dst, torch.bfloat16, "dst")
+    if M is None:
+        M = src_rows.numel() if src_rows is not None else (dst_rows.numel() if dst_rows is not None else src.shape[0])
+    H = src.shape[-1]
+    rc = _cabi.lib().bagel_copy_rows_bf16(_ptr(src), src.stride(0), _ptr(src_rows), _ptr(dst), dst.stride(0),
+                                          _ptr(dst_rows), M, H, _stream())
+    _cabi.check(rc, "bagel_copy_rows_bf16")
+    return dst
+
+
+def latent_embed_add(proj, t_emb, pos_table, pos_ids, seq, dst_rows):
+    M, H = proj.shape
+    _req(pos_ids, torch.int64, "pos_ids")
+    rc = _cabi.lib().bagel_latent_embed_add(_ptr(proj), proj.stride(0), _ptr(t_emb), _ptr(pos_table), pos_table.stride(0),
+                                            _ptr(pos_ids), _ptr(seq), seq.stride(0), _ptr(dst_rows), M, H, _stream())
+    _cabi.check(rc, "bagel_latent_embed_add")
+
+
+RENORM = {"global": 0, "channel": 1, "text_channel": 2}
+
+
+def cfg_euler_step(v, v_text, v_img, rows, x, norms_ws, cfg_text_scale, cfg_img_scale, renorm_min, renorm_type, dt):
+    _req(x, torch.float32, "x")
+    M, Cc = x.shape
+    rc = _cabi.lib().bagel_cfg_euler_step(_ptr(v), _ptr(v_text), _ptr(v_img), v.stride(0), _ptr(rows), _ptr(x),
+                                          _ptr(norms_ws), M, Cc, float(cfg_text_scale), float(cfg_img_scale),
+                                          float(renorm_min), RENORM[renorm_type], float(dt), _stream())
+    _cabi.check(rc, "bagel_cfg_euler_step")
+
+
+def cast_f32_to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    rc = _cabi.lib().bagel_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
+    _cabi.check(rc, "bagel_cast_f32_to_bf16")
+    return out

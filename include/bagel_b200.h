@@ -58,6 +58,62 @@ int bagel_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
                     int N, int K, const void* bias, const void* resid, long long ldr, const int* row_map,
                     int epilogue, void* stream);
 
+/* Packed variable-length attention forward; same contract as flash_attn_varlen_func as the reference calls it
+ * (modeling/bagel/qwen2_navit.py:361-370, 579-588; modeling/bagel/siglip_navit.py:232-241):
+ *   q [total_q, Hq, D], k/v [total_k, Hk, D], out [total_q, Hq, D] bf16 (row strides ld_* in elements);
+ *   cu_seqlens_q / cu_seqlens_k int32 [batch+1] DEVICE arrays; Hq % Hk == 0 (GQA); D in {64, 128};
+ *   causal != 0: bottom-right aligned mask (query i sees keys <= i + Lk - Lq), as flash-attn >= 2.1;
+ *   softmax in fp32, scale = softmax_scale (reference default D^-0.5). max_seqlen_q sizes the grid (host int,
+ *   exactly what the reference passes); max_seqlen_k is accepted for signature parity and unused. */
+int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,
+                          const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
+                          int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,
+                          float softmax_scale, long long ld_q, long long ld_k, long long ld_v, long long ld_out,
+                          void* stream);
+
+/* y = bf16(w_e * bf16(x * rsqrt(mean(x^2) + eps))), e = expert[row] ? w1 : w0 (expert / w1 may be NULL).
+ * Qwen2RMSNorm (modeling/qwen2/modeling_qwen2.py:54-59) with the MoT row routing of
+ * modeling/bagel/qwen2_navit.py:781-787, 808-815, 1075-1082. x, y bf16 [N, H]. */
+int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, const void* w1, const uint8_t* expert, void* y,
+                       long long ldy, int N, int H, float eps, void* stream);
+
+/* cos/sin[N, half] = cos/sin(float(pos[r]) * inv_freq[c]), optionally rounded to bf16 values
+ * (Qwen2RotaryEmbedding.forward, modeling/qwen2/modeling_qwen2.py:130-150; halves are duplicated there). */
+int bagel_rope_table(const long long* pos, const float* inv_freq, float* cos_t, float* sin_t, int N, int half,
+                     int round_bf16, void* stream);
+
+/* Per-head RMSNorm(q,k) + RoPE + bf16 cast + placement of K/V rows into the merged KV buffer
+ * (PackedAttentionMoT.forward_inference, modeling/bagel/qwen2_navit.py:518-519, 542-557, 559-574).
+ *   qkv [N, (Hq+2Hk)*D] bf16; q_out [N, Hq*D]; k_out / v_out [rows, Hk*D] written at row kv_rows[r] (NULL: r);
+ *   *_w0 und-expert norm weights [D], *_w1 gen-expert (NULL when not MoT), expert[N] routing flags (may be NULL);
+ *   fp32_flow: 1 = mode "gen" numerics (fp32 norm+RoPE, single bf16 cast), 0 = mode "und" (bf16 at every op). */
+int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void* q_w0, const void* k_w0, const void* q_w1,
+                       const void* k_w1, const uint8_t* expert, const float* cos_t, const float* sin_t, void* q_out,
+                       long long ld_q, void* k_out, void* v_out, long long ld_kv, const int* kv_rows, int N, int Hq,
+                       int Hk, int D, float eps, int fp32_flow, void* stream);
+
+/* dst[dst_rows[i]] = src[src_rows[i]] for i < M (either map may be NULL = identity); bf16 rows of H elements.
+ * Token-embedding lookup (modeling/bagel/bagel.py:277, 796), modality gathers (qwen2_navit.py:526-548) and
+ * cached-KV placement (qwen2_navit.py:565-569). */
+int bagel_copy_rows_bf16(const void* src, long long lds, const int* src_rows, void* dst, long long ldd,
+                         const int* dst_rows, int M, int H, void* stream);
+
+/* seq[dst_rows[i]] = bf16(bf16(proj[i] + t_emb) + pos_table[pos_ids[i]])  (modeling/bagel/bagel.py:801-806). */
+int bagel_latent_embed_add(const void* proj, long long ldp, const void* t_emb, const void* pos_table, long long ldt,
+                           const long long* pos_ids, void* seq, long long lds, const int* dst_rows, int M, int H,
+                           void* stream);
+
+/* CFG combine + renorm + Euler update, x fp32 [M, C] in place (modeling/bagel/bagel.py:873-907, :746).
+ *   v / v_text / v_img: bf16 llm2vae outputs of the main / text-dropped / image-dropped branches (row pitch ldv),
+ *   latent token i lives at row rows[i] (NULL: i). v_text NULL or cfg_text_scale <= 1: plain x -= bf16(v*dt).
+ *   renorm_type 0 "global" (needs norms_ws fp32[2]), 1 "channel", 2 "text_channel". */
+int bagel_cfg_euler_step(const void* v, const void* v_text, const void* v_img, long long ldv, const int* rows,
+                         float* x, float* norms_ws, int M, int C, float cfg_text_scale, float cfg_img_scale,
+                         float renorm_min, int renorm_type, float dt, void* stream);
+
+/* y[i] = bf16(x[i]) — the autocast cast in front of vae2llm (modeling/bagel/bagel.py:803). */
+int bagel_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

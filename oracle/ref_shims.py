@@ -25,7 +25,14 @@ def reference_available() -> bool:
 
 def cpu_varlen_attention(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q=None, max_seqlen_k=None,
                          causal=False, **_unused):
-    """q [Sq,Hq,D], k/v [Sk,Hk,D] bf16 -> [Sq,Hq,D]; softmax in fp32, output cast back to q.dtype."""
+    """q [Sq,Hq,D], k/v [Sk,Hk,D] bf16 -> [Sq,Hq,D]; softmax in fp32, output cast back to q.dtype.
+    Runs with autocast disabled: the reference calls this under torch.autocast, which would silently turn
+    the fp32 matmuls below into bf16 ones (flash-attn accumulates in fp32 regardless of autocast)."""
+    with torch.autocast("cpu", enabled=False):
+        return _cpu_varlen_attention(q, k, v, cu_seqlens_q, cu_seqlens_k, causal)
+
+
+def _cpu_varlen_attention(q, k, v, cu_seqlens_q, cu_seqlens_k, causal):
     out = torch.empty_like(q)
     hq, hk = q.shape[1], k.shape[1]
     rep = hq // hk
@@ -107,3 +114,11 @@ def make_llm_config(ns, **kw):
     if getattr(cfg, "rope_theta", None) is None:
         cfg.rope_theta = kw.get("rope_theta", 1000000.0)
     return cfg
+
+
+def cast_parameters(module, dtype):
+    """bf16 weights the way app.py:111 gets them (accelerate `dtype=` casts checkpoint tensors only):
+    parameters are cast, non-persistent buffers such as rotary inv_freq stay fp32."""
+    for p in module.parameters():
+        p.data = p.data.to(dtype)
+    return module

@@ -53,8 +53,12 @@ M, N, K = 512, 3584, 512
 a = torch.randn(M, K, device=dev).to(torch.bfloat16); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
 res = torch.randn(M, N, device=dev).to(torch.bfloat16)
 out = ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID); torch.cuda.synchronize()
-ref = res.float() + ref_mm(a, w).to(torch.bfloat16).float()
-ok &= check("resid", out, ref, tol_ulp=4.0)
+mm = ref_mm(a, w)
+ref = res.float() + mm.to(torch.bfloat16).float()
+# tolerance is relative to the operands (res, mm), not to the possibly-cancelling sum
+err = (out.float() - ref).abs(); tol = (res.float().abs() + mm.abs()) * 2.0 ** -8 * 2 + 2e-3
+print(f"[resid] max_abs_err={err.max().item():.4e} bad={int((err > tol).sum())}/{out.numel()}", flush=True)
+ok &= bool((err <= tol).all())
 
 # swiglu epilogue
 M, I, K = 512, 1024, 256
