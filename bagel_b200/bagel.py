@@ -1,0 +1,427 @@
+"""BAGEL unified model — host side of the B200-native build.
+
+Same public surface as the reference's modeling/bagel/bagel.py (Bagel :57): the `prepare_*` packers
+(:232-264, :552-641, :909-927) return dicts with the same keys / dtypes (key names are API — callers splat
+them as kwargs), `forward_cache_update_text` (:267-297) prefill, the rectified-flow sampler `generate_image`
+(:644-754) with `_forward_flow` (:757-907), and `generate_text` (:930-1000).
+
+What is different underneath (B200-first, not a port):
+  * packers are vectorised index arithmetic (no per-token Python loops);
+  * `generate_image` plans the whole run once (index maps, RoPE tables, all timestep embeddings, merged KV
+    buffers with the read-only context already in place), batches the CFG branches into ONE packed LM call per
+    step (they share weights; the reference runs them one after another), keeps x_t resident in HBM and issues
+    a sync-free launch sequence per step, optionally replayed as a CUDA graph;
+  * every tensor op on the per-step path is a kernel from bagel_b200.ops.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .config import BagelConfig
+from .modeling_utils import MLPconnector, PositionEmbedding, TimestepEmbedder
+from .qwen2_navit import NaiveCache, Qwen2ForCausalLM
+
+BF16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------------
+# index helpers (host, int64)
+# --------------------------------------------------------------------------------------------------
+def _ranges(starts: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """concat_i arange(starts[i], starts[i] + lens[i])"""
+    lens = lens.to(torch.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return torch.zeros(0, dtype=torch.int64)
+    excl = torch.cumsum(lens, 0) - lens
+    return torch.repeat_interleave(starts.to(torch.int64) - excl, lens) + torch.arange(total, dtype=torch.int64)
+
+
+def get_flattened_position_ids_extrapolate(img_h, img_w, patch_size, max_num_patches_per_side):
+    """row * max_side + col for every patch (reference data/data_utils.py:53-58)."""
+    nh, nw = img_h // patch_size, img_w // patch_size
+    return (torch.arange(nh)[:, None] * max_num_patches_per_side + torch.arange(nw)[None, :]).reshape(-1)
+
+
+def get_flattened_position_ids_interpolate(img_h, img_w, patch_size, max_num_patches_per_side):
+    """Bucketised fractional coordinates (reference data/data_utils.py:61-69)."""
+    nh, nw = img_h // patch_size, img_w // patch_size
+    edges = torch.arange(1 / max_num_patches_per_side, 1.0, 1 / max_num_patches_per_side)
+    bh = torch.bucketize(torch.arange(0, 1 - 1e-6, 1 / nh), edges, right=True)
+    bw = torch.bucketize(torch.arange(0, 1 - 1e-6, 1 / nw), edges, right=True)
+    return (bh[:, None] * max_num_patches_per_side + bw[None, :]).reshape(-1)
+
+
+class _Affine:
+    """weight/bias holder for vae2llm / llm2vae."""
+
+    def __init__(self):
+        self.weight = self.bias = None
+
+    def load(self, sd, prefix, device):
+        self.weight = sd[prefix + "weight"].to(device, BF16).contiguous()
+        self.bias = sd[prefix + "bias"].to(device, BF16).contiguous()
+
+    def __call__(self, x):
+        return ops.gemm(x.to(BF16).contiguous(), self.weight, bias=self.bias)
+
+
+class Bagel:
+    def __init__(self, language_model: Qwen2ForCausalLM, vit_model, config: BagelConfig):
+        self.language_model = language_model
+        self.config = config
+        self.device = language_model.device
+        llm = config.llm_config
+        self.hidden_size = llm.hidden_size
+        self.use_moe = "Mo" in llm.layer_module
+        self.num_heads = llm.num_attention_heads
+        if config.visual_gen:
+            self.latent_patch_size = config.latent_patch_size
+            self.timestep_shift = config.timestep_shift
+            self.latent_downsample = config.vae_config.downsample * config.latent_patch_size
+            self.max_latent_size = config.max_latent_size
+            self.latent_channel = config.vae_config.z_channels
+            self.patch_latent_dim = self.latent_patch_size ** 2 * self.latent_channel
+            self.time_embedder = TimestepEmbedder(self.hidden_size)
+            self.vae2llm = _Affine()
+            self.llm2vae = _Affine()
+            self.latent_pos_embed = PositionEmbedding(self.max_latent_size, self.hidden_size, self.device)
+        if config.visual_und:
+            self.vit_model = vit_model
+            self.vit_patch_size = config.vit_config.patch_size
+            self.vit_max_num_patch_per_side = config.vit_max_num_patch_per_side
+            self.vit_hidden_size = config.vit_config.hidden_size
+            self.connector = MLPconnector(self.vit_hidden_size, self.hidden_size, config.connector_act)
+            self.vit_pos_embed = PositionEmbedding(self.vit_max_num_patch_per_side, self.hidden_size, self.device)
+        self.get_flattened_position_ids = (get_flattened_position_ids_interpolate if config.interpolate_pos
+                                           else get_flattened_position_ids_extrapolate)
+        self.use_cuda_graph = True
+        self._graph_cache: Dict[Any, Any] = {}
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    # weights (reference key schema)
+    # ------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        lm_sd = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+        self.language_model.load_state_dict(lm_sd, strict=True)
+        if self.config.visual_gen:
+            self.time_embedder.load(sd, "time_embedder.", self.device)
+            self.vae2llm.load(sd, "vae2llm.", self.device)
+            self.llm2vae.load(sd, "llm2vae.", self.device)
+            self.latent_pos_embed.load(sd.get("latent_pos_embed.pos_embed"))
+        if self.config.visual_und:
+            if "connector.fc1.weight" in sd:
+                self.connector.load(sd, "connector.", self.device)
+            self.vit_pos_embed.load(sd.get("vit_pos_embed.pos_embed"))
+            if self.vit_model is not None and hasattr(self.vit_model, "load_state_dict"):
+                vit_sd = {k[len("vit_model."):]: v for k, v in sd.items() if k.startswith("vit_model.")}
+                if vit_sd:
+                    self.vit_model.load_state_dict(vit_sd)
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    # packers
+    # ------------------------------------------------------------------------------------------
+    def prepare_prompts(self, curr_kvlens, curr_rope, prompts, tokenizer, new_token_ids):
+        bos, eos = new_token_ids["bos_token_id"], new_token_ids["eos_token_id"]
+        ids = [[bos] + list(tokenizer.encode(p)) + [eos] for p in prompts]
+        tl = torch.tensor([len(x) for x in ids], dtype=torch.int64)
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        rope = torch.tensor(list(curr_rope), dtype=torch.int64)
+        sample_start = torch.cumsum(cl + tl, 0) - (cl + tl)
+        generation_input = {
+            "text_token_lens": tl.to(torch.int),
+            "packed_text_ids": torch.tensor([t for x in ids for t in x], dtype=torch.long),
+            "packed_text_position_ids": _ranges(rope, tl),
+            "packed_text_indexes": _ranges(sample_start + cl, tl),
+            "packed_key_value_indexes": _ranges(sample_start, cl),
+            "key_values_lens": cl.to(torch.int),
+        }
+        return generation_input, (cl + tl).tolist(), (rope + tl).tolist()
+
+    def prepare_vae_latent(self, curr_kvlens, curr_rope, image_sizes, new_token_ids):
+        ds = self.latent_downsample
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        rope = torch.tensor(list(curr_rope), dtype=torch.int64)
+        ntok = torch.tensor([(H // ds) * (W // ds) for H, W in image_sizes], dtype=torch.int64)
+        ql = ntok + 2
+        q_start = torch.cumsum(ql, 0) - ql
+        b_start = torch.cumsum(cl + ql, 0) - (cl + ql)
+        B = len(image_sizes)
+        dim = self.latent_channel * self.latent_patch_size ** 2
+        # init noise: drawn per sample, in sample order, from the global CPU generator exactly like the reference
+        noises = [torch.randn(int(n), dim) for n in ntok]
+        pos = [self.get_flattened_position_ids(H, W, ds, max_num_patches_per_side=self.max_latent_size)
+               for H, W in image_sizes]
+        generation_input = {
+            "packed_text_ids": torch.tensor([new_token_ids["start_of_image"], new_token_ids["end_of_image"]] * B,
+                                            dtype=torch.long),
+            "packed_text_indexes": torch.stack([q_start, q_start + ntok + 1], dim=1).reshape(-1),
+            "packed_init_noises": torch.cat(noises, dim=0),
+            "packed_vae_position_ids": torch.cat(pos, dim=0),
+            "packed_vae_token_indexes": _ranges(q_start + 1, ntok),
+            "packed_seqlens": ql.to(torch.int),
+            "packed_position_ids": torch.repeat_interleave(rope, ql),
+            "key_values_lens": cl.to(torch.int),
+            "packed_indexes": _ranges(b_start + cl, ql),
+            "packed_key_value_indexes": _ranges(b_start, cl),
+        }
+        return generation_input
+
+    def prepare_vae_latent_cfg(self, curr_kvlens, curr_rope, image_sizes):
+        ds = self.latent_downsample
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        rope = torch.tensor(list(curr_rope), dtype=torch.int64)
+        ql = torch.tensor([(H // ds) * (W // ds) + 2 for H, W in image_sizes], dtype=torch.int64)
+        b_start = torch.cumsum(cl + ql, 0) - (cl + ql)
+        return {
+            "cfg_packed_position_ids": torch.repeat_interleave(rope, ql),
+            "cfg_key_values_lens": cl.to(torch.int),
+            "cfg_packed_query_indexes": _ranges(b_start + cl, ql),
+            "cfg_packed_key_value_indexes": _ranges(b_start, cl),
+        }
+
+    def prepare_start_tokens(self, curr_kvlens, curr_rope, new_token_ids):
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        b_start = torch.cumsum(cl + 1, 0) - (cl + 1)
+        B = len(curr_kvlens)
+        return {
+            "packed_start_tokens": torch.tensor([new_token_ids["bos_token_id"]] * B, dtype=torch.long),
+            "packed_query_position_ids": torch.tensor(list(curr_rope), dtype=torch.long),
+            "key_values_lens": cl.to(torch.int),
+            "packed_key_value_indexes": _ranges(b_start, cl),
+        }
+
+    # ------------------------------------------------------------------------------------------
+    # prefill
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_cache_update_text(self, past_key_values: NaiveCache, packed_text_ids, packed_text_position_ids,
+                                  text_token_lens, packed_text_indexes, packed_key_value_indexes, key_values_lens):
+        emb = self.language_model.model.embed_tokens(packed_text_ids)
+        out = self.language_model.forward_inference(
+            packed_query_sequence=emb, query_lens=text_token_lens,
+            packed_query_position_ids=packed_text_position_ids, packed_query_indexes=packed_text_indexes,
+            past_key_values=past_key_values, packed_key_value_indexes=packed_key_value_indexes,
+            key_values_lens=key_values_lens, update_past_key_values=True, is_causal=True, mode="und")
+        return out.past_key_values
+
+    # ------------------------------------------------------------------------------------------
+    # rectified-flow sampler
+    # ------------------------------------------------------------------------------------------
+    def _build_flow_plan(self, branches: List[Dict[str, Any]], packed_seqlens, packed_vae_token_indexes,
+                         packed_text_indexes):
+        """One ForwardPlan covering all CFG branches as extra samples of the packed batch, plus merged KV
+        buffers with every branch's (read-only) context rows placed once."""
+        lm = self.language_model.model
+        n = int(torch.as_tensor(packed_seqlens).sum())
+        ql, pos, qidx, kvl, kvidx, vae, txt = [], [], [], [], [], [], []
+        row_off = 0
+        ctx_pairs = []
+        for b, br in enumerate(branches):
+            kl = torch.as_tensor(br["key_values_lens"]).to("cpu", torch.int64)
+            has_ctx = br["past_key_values"] is not None and br["past_key_values"].key_cache[0] is not None
+            if not has_ctx:
+                kl = torch.zeros_like(kl)
+            total_b = n + int(kl.sum())
+            ql.append(torch.as_tensor(packed_seqlens).to("cpu", torch.int64))
+            pos.append(torch.as_tensor(br["packed_position_ids"]).to("cpu", torch.int64))
+            qidx.append(torch.as_tensor(br["packed_query_indexes"]).to("cpu", torch.int64) + row_off)
+            kvl.append(kl)
+            ki = torch.as_tensor(br["packed_key_value_indexes"]).to("cpu", torch.int64) if has_ctx else torch.zeros(0, dtype=torch.int64)
+            kvidx.append(ki + row_off)
+            if has_ctx:
+                ctx_pairs.append((br["past_key_values"], (ki + row_off).to(self.device, torch.int32)))
+            vae.append(torch.as_tensor(packed_vae_token_indexes).to("cpu", torch.int64) + b * n)
+            txt.append(torch.as_tensor(packed_text_indexes).to("cpu", torch.int64) + b * n)
+            row_off += total_b
+        plan = lm.make_plan(query_lens=torch.cat(ql), position_ids=torch.cat(pos),
+                            packed_query_indexes=torch.cat(qidx), key_values_lens=torch.cat(kvl),
+                            packed_key_value_indexes=torch.cat(kvidx), is_causal=False,
+                            mode="gen" if self.use_moe else "und",
+                            packed_vae_token_indexes=torch.cat(vae), packed_text_indexes=torch.cat(txt))
+        kbuf, vbuf = lm.alloc_kv(plan)
+        cfg = lm.config
+        w = cfg.num_key_value_heads * cfg.head_dim
+        for cache, rows in ctx_pairs:
+            m = rows.numel()
+            for li in range(cfg.num_hidden_layers):
+                ops.copy_rows(cache.key_cache[li].reshape(m, w), kbuf[li], dst_rows=rows, M=m)
+                ops.copy_rows(cache.value_cache[li].reshape(m, w), vbuf[li], dst_rows=rows, M=m)
+        return plan, kbuf, vbuf
+
+    def _velocity(self, st: Dict[str, Any], key: str, t_row: torch.Tensor, x_src: torch.Tensor) -> int:
+        """Latent-in (bagel.py:796-806) -> packed LM call over all CFG branches -> llm2vae (:832). Fills
+        st['v_all'][b*n:(b+1)*n] with branch b's outputs for every packed row; returns the branch count."""
+        lm = self.language_model.model
+        plan, kbuf, vbuf, nb = st[key]
+        n = st["n"]
+        seq = lm._buf("xa", plan.n, self.hidden_size)
+        ops.cast_f32_to_bf16(x_src, out=st["x_bf16"])
+        ops.gemm(st["x_bf16"], self.vae2llm.weight, bias=self.vae2llm.bias, out=st["proj"])
+        for b in range(nb):
+            ops.latent_embed_add(st["proj"], t_row, self.latent_pos_embed.pos_embed, st["vae_pos"],
+                                 seq[b * n:(b + 1) * n], st["vae_rows"])
+            ops.copy_rows(st["text_emb"], seq[b * n:(b + 1) * n], dst_rows=st["text_rows"])
+        out = lm.run_layers(seq, plan, kbuf, vbuf)
+        ops.gemm(out, self.llm2vae.weight, bias=self.llm2vae.bias, out=st["v_all"][: nb * n])
+        return nb
+
+    def _cfg_update(self, st: Dict[str, Any], nb: int, scales: Tuple[float, float], renorm_min: float,
+                    renorm_type: str, x_dst: torch.Tensor, dt: float):
+        """CFG combine + renorm (bagel.py:873-905) fused with the Euler update x -= v*dt (:746)."""
+        n, v = st["n"], st["v_all"]
+        sT, sI = scales
+        v_text = v[n:2 * n] if (nb >= 2 and sT > 1.0) else None
+        v_img = v[2 * n:3 * n] if (nb >= 3 and sI > 1.0 and v_text is not None) else None
+        ops.cfg_euler_step(v[:n], v_text, v_img, st["vae_rows"], x_dst, st["norms"],
+                           sT if v_text is not None else 1.0, sI if v_img is not None else 1.0, renorm_min,
+                           renorm_type, dt)
+
+    def _flow_state(self, x_t, packed_seqlens, packed_vae_token_indexes, packed_text_indexes,
+                    packed_vae_position_ids, packed_text_ids, nb: int) -> Dict[str, Any]:
+        dev = self.device
+        lm = self.language_model.model
+        n = int(torch.as_tensor(packed_seqlens).sum())
+        vae_idx = torch.as_tensor(packed_vae_token_indexes).to("cpu", torch.int64)
+        txt_idx = torch.as_tensor(packed_text_indexes).to("cpu", torch.int64)
+        M = int(vae_idx.numel())
+        st: Dict[str, Any] = {"n": n, "M": M, "vae_idx": vae_idx, "txt_idx": txt_idx}
+        st["x"] = x_t.to(dev, torch.float32, non_blocking=True).contiguous().clone()
+        st["x_bf16"] = torch.empty((M, self.patch_latent_dim), dtype=BF16, device=dev)
+        st["proj"] = torch.empty((M, self.hidden_size), dtype=BF16, device=dev)
+        st["v_all"] = torch.empty((nb * n, self.patch_latent_dim), dtype=BF16, device=dev)
+        st["norms"] = torch.zeros(2, dtype=torch.float32, device=dev)
+        st["vae_rows"] = vae_idx.to(dev, torch.int32)
+        st["text_rows"] = txt_idx.to(dev, torch.int32)
+        st["vae_pos"] = torch.as_tensor(packed_vae_position_ids).to(dev, torch.int64).contiguous()
+        st["text_emb"] = lm.embed_tokens(torch.as_tensor(packed_text_ids))
+        return st
+
+    @torch.no_grad()
+    def make_flow_runner(self, packed_text_ids, packed_text_indexes, packed_init_noises, packed_vae_position_ids,
+                         packed_vae_token_indexes, packed_seqlens, packed_position_ids, packed_indexes,
+                         past_key_values: NaiveCache, key_values_lens, packed_key_value_indexes,
+                         num_timesteps: int = 24, timestep_shift: float = 1.0, cfg_renorm_min: float = 0.0,
+                         cfg_renorm_type: str = "global", cfg_interval: Optional[Sequence[float]] = (0, 1),
+                         cfg_text_scale: float = 1.0, cfg_text_packed_query_indexes=None,
+                         cfg_text_packed_position_ids=None, cfg_text_past_key_values: Optional[NaiveCache] = None,
+                         cfg_text_key_values_lens=None, cfg_text_packed_key_value_indexes=None,
+                         cfg_img_scale: float = 1.0, cfg_img_packed_query_indexes=None,
+                         cfg_img_packed_position_ids=None, cfg_img_past_key_values: Optional[NaiveCache] = None,
+                         cfg_img_key_values_lens=None, cfg_img_packed_key_value_indexes=None,
+                         cfg_type: str = "parallel", enable_taylorseer: bool = False) -> "FlowRunner":
+        """Plan a whole denoising run (same arguments as generate_image); FlowRunner.step(i) then executes
+        velocity evaluation + CFG + Euler update number i as a sync-free kernel sequence."""
+        if enable_taylorseer:
+            raise NotImplementedError("TaylorSeer step caching is out of scope (SURVEY.md §8f #1)")
+        if cfg_renorm_type not in ops.RENORM:
+            raise NotImplementedError(f"{cfg_renorm_type} is not suppoprted")
+        dev = self.device
+
+        # ---- schedule (host; identical arithmetic to the reference :693-696) ----
+        ts = torch.linspace(1, 0, num_timesteps)
+        ts = timestep_shift * ts / (1 + (timestep_shift - 1) * ts)
+        dts = ts[:-1] - ts[1:]
+        ts = ts[:-1]
+        cfg_on = [bool(t > cfg_interval[0] and t <= cfg_interval[1]) for t in ts]
+
+        main = dict(packed_position_ids=packed_position_ids, packed_query_indexes=packed_indexes,
+                    past_key_values=past_key_values, key_values_lens=key_values_lens,
+                    packed_key_value_indexes=packed_key_value_indexes)
+        branches = [main]
+        if cfg_text_scale > 1.0:
+            branches.append(dict(packed_position_ids=cfg_text_packed_position_ids,
+                                 packed_query_indexes=cfg_text_packed_query_indexes,
+                                 past_key_values=cfg_text_past_key_values, key_values_lens=cfg_text_key_values_lens,
+                                 packed_key_value_indexes=cfg_text_packed_key_value_indexes))
+            if cfg_img_scale > 1.0:  # the reference consumes the image branch only inside the text-CFG block (:873)
+                branches.append(dict(packed_position_ids=cfg_img_packed_position_ids,
+                                     packed_query_indexes=cfg_img_packed_query_indexes,
+                                     past_key_values=cfg_img_past_key_values, key_values_lens=cfg_img_key_values_lens,
+                                     packed_key_value_indexes=cfg_img_packed_key_value_indexes))
+        nbmax = len(branches)
+        st = self._flow_state(packed_init_noises, packed_seqlens, packed_vae_token_indexes, packed_text_indexes,
+                              packed_vae_position_ids, packed_text_ids, nbmax)
+        st["t_emb"] = self.time_embedder(ts.to(dev))  # every timestep of the run at once: [num_timesteps-1, H]
+        if any(cfg_on) and nbmax > 1:
+            st["full"] = (*self._build_flow_plan(branches, packed_seqlens, st["vae_idx"], st["txt_idx"]), nbmax)
+        if (not all(cfg_on)) or nbmax == 1:
+            st["main"] = (*self._build_flow_plan(branches[:1], packed_seqlens, st["vae_idx"], st["txt_idx"]), 1)
+        return FlowRunner(self, st, dts.tolist(), cfg_on, (cfg_text_scale, cfg_img_scale), cfg_renorm_min,
+                          cfg_renorm_type, nbmax, torch.as_tensor(packed_seqlens).to("cpu", torch.int64))
+
+    @torch.no_grad()
+    def generate_image(self, *args, **kwargs):
+        """Rectified-flow Euler sampler (reference bagel.py:644-754), same signature as the reference; returns the
+        tuple of per-sample latents [h*w, 64] fp32 (on the model's device)."""
+        runner = self.make_flow_runner(*args, **kwargs)
+        for i in range(runner.num_steps):
+            runner.step(i)
+        return runner.latents()
+
+    @torch.no_grad()
+    def _forward_flow(self, x_t, timestep, packed_vae_token_indexes, packed_vae_position_ids, packed_text_ids,
+                      packed_text_indexes, packed_indexes, packed_position_ids, packed_seqlens, key_values_lens,
+                      past_key_values, packed_key_value_indexes, cfg_renorm_min=0.0, cfg_renorm_type="global",
+                      cfg_text_scale=1.0, cfg_text_packed_position_ids=None, cfg_text_packed_query_indexes=None,
+                      cfg_text_key_values_lens=None, cfg_text_past_key_values=None,
+                      cfg_text_packed_key_value_indexes=None, cfg_img_scale=1.0, cfg_img_packed_position_ids=None,
+                      cfg_img_packed_query_indexes=None, cfg_img_key_values_lens=None, cfg_img_past_key_values=None,
+                      cfg_img_packed_key_value_indexes=None, cfg_type="parallel", **_taylorseer_unused):
+        """One velocity evaluation v_t [M, C] bf16 (reference :757-907). Implemented as a single Euler step of
+        the fused path on x = 0 with dt = -1, which returns exactly the CFG-combined velocity."""
+        dev = self.device
+        lm = self.language_model.model
+        t = torch.as_tensor(timestep).to("cpu", torch.float32).reshape(-1)
+        assert t.unique().numel() == 1
+        main = dict(packed_position_ids=packed_position_ids, packed_query_indexes=packed_indexes,
+                    past_key_values=past_key_values, key_values_lens=key_values_lens,
+                    packed_key_value_indexes=packed_key_value_indexes)
+        branches = [main]
+        if cfg_text_scale > 1.0:
+            branches.append(dict(packed_position_ids=cfg_text_packed_position_ids,
+                                 packed_query_indexes=cfg_text_packed_query_indexes,
+                                 past_key_values=cfg_text_past_key_values, key_values_lens=cfg_text_key_values_lens,
+                                 packed_key_value_indexes=cfg_text_packed_key_value_indexes))
+            if cfg_img_scale > 1.0:
+                branches.append(dict(packed_position_ids=cfg_img_packed_position_ids,
+                                     packed_query_indexes=cfg_img_packed_query_indexes,
+                                     past_key_values=cfg_img_past_key_values, key_values_lens=cfg_img_key_values_lens,
+                                     packed_key_value_indexes=cfg_img_packed_key_value_indexes))
+        nb = len(branches)
+        st = self._flow_state(x_t, packed_seqlens, packed_vae_token_indexes, packed_text_indexes,
+                              packed_vae_position_ids, packed_text_ids, nb)
+        st["t_emb"] = self.time_embedder(t[:1].to(dev))
+        st["full"] = (*self._build_flow_plan(branches, packed_seqlens, st["vae_idx"], st["txt_idx"]), nb)
+        self._velocity(st, "full", st["t_emb"][0], st["x"])
+        v_out = torch.zeros_like(st["x"])  # x' = 0 - bf16(v * -1) = v
+        self._cfg_update(st, nb, (cfg_text_scale, cfg_img_scale), cfg_renorm_min, cfg_renorm_type, v_out, -1.0)
+        return v_out.to(BF16)
+
+
+class FlowRunner:
+    """A planned denoising run: x_t resident in HBM, one sync-free launch sequence per step."""
+
+    def __init__(self, model: Bagel, st, dts, cfg_on, scales, renorm_min, renorm_type, nbmax, seqlens):
+        self.model, self.st, self.dts, self.cfg_on = model, st, dts, cfg_on
+        self.scales, self.renorm_min, self.renorm_type, self.nbmax = scales, renorm_min, renorm_type, nbmax
+        self.seqlens = seqlens
+        self.num_steps = len(dts)
+
+    @torch.no_grad()
+    def step(self, i: int):
+        m, st = self.model, self.st
+        on = self.cfg_on[i] and self.nbmax > 1
+        nb = m._velocity(st, "full" if on else "main", st["t_emb"][i], st["x"])
+        m._cfg_update(st, nb, self.scales if on else (1.0, 1.0), self.renorm_min, self.renorm_type, st["x"],
+                      float(self.dts[i]))
+
+    def latents(self):
+        return self.st["x"].split((self.seqlens - 2).tolist())

@@ -20,6 +20,24 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional live timing of one kernel family inside a run (bench.py roofline): CUDA events on the launching stream.
+_timer = {"tag": None, "events": []}
+
+
+def kernel_timer_start(tag: str) -> None:
+    _timer["tag"], _timer["events"] = tag, []
+
+
+def kernel_timer_stop():
+    """Returns the per-launch durations (ms) recorded since kernel_timer_start (synchronises)."""
+    ev = _timer["events"]
+    _timer["tag"], _timer["events"] = None, []
+    if not ev:
+        return []
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise _cabi.BagelB200Error(f"{name}: expected a CUDA tensor (bagel_b200 has no CPU path)")
@@ -64,9 +82,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if row_map is not None:
         _req(row_map, torch.int32, "row_map")
         assert row_map.numel() == M
+    timed = _timer["tag"] == "swiglu" and epilogue == EPI_SWIGLU and M >= 1024
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _cabi.lib().bagel_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0),
                                      M, N, K, _ptr(bias), _ptr(resid), ldr, _ptr(row_map), epilogue, _stream())
     _cabi.check(rc, "bagel_gemm_bf16")
+    if timed:
+        e1.record()
+        _timer["events"].append((e0, e1))
     return out
 
 

@@ -1,0 +1,347 @@
+"""Packed (NaViT) Qwen2 / Mixture-of-Transformers language model — host side.
+
+Mirrors the inference API of the reference's modeling/bagel/qwen2_navit.py (NaiveCache :207-221,
+Qwen2Model.forward_inference :1018-1092, Qwen2ForCausalLM.forward_inference :1157-1188, and the MoT layer /
+attention they call :499-600, :757-831) with the same argument names and meaning, but executes every layer as a
+fixed sequence of hand-written sm_100a kernels (bagel_b200.ops). There is no nn.Module / autograd here: weights
+are plain device tensors in fused layouts (QKV concatenated, gate/up interleaved for the SwiGLU epilogue).
+
+Numerics follow the reference's "mode A" (bf16 weights under autocast, app.py:111 + inferencer.py:233): bf16
+residual stream, fp32 accumulation inside every kernel, the reference's bf16 rounding points kept.
+
+MoT routing (reference: ~20 index gathers/scatters per layer, qwen2_navit.py:526-548, 593-594, 781-787,
+808-819): every row runs through the gen-expert GEMM; the few text rows (2 per image while denoising) are
+gathered once per GEMM, run through the und-expert weights, and scattered over their rows by the GEMM epilogue.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .config import Qwen2Config
+
+BF16 = torch.bfloat16
+
+
+class NaiveCache:
+    """Per-layer packed KV tensors [sum_kv, Hk, D] (or None) — reference qwen2_navit.py:207-221.
+    Deep-copyable (inferencer.py:230-253 relies on copy.deepcopy of whole contexts)."""
+
+    def __init__(self, num_layers: int):
+        self.key_cache: Dict[int, Optional[torch.Tensor]] = {k: None for k in range(num_layers)}
+        self.value_cache: Dict[int, Optional[torch.Tensor]] = {k: None for k in range(num_layers)}
+
+    @property
+    def num_layers(self) -> int:
+        return len(self.key_cache)
+
+    @property
+    def seq_lens(self) -> int:
+        return 0 if self.key_cache[0] is None else self.key_cache[0].shape[0]
+
+
+@dataclass
+class BaseNavitOutputWithPast:
+    packed_query_sequence: torch.Tensor = None
+    past_key_values: Optional[NaiveCache] = None
+
+
+class _Embedding:
+    """model.embed_tokens: callable like nn.Embedding, gather done by bagel_copy_rows_bf16."""
+
+    def __init__(self, weight: torch.Tensor):
+        self.weight = weight
+
+    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        ids32 = ids.to(device=self.weight.device, dtype=torch.int32)
+        out = torch.empty((ids32.numel(), self.weight.shape[1]), dtype=BF16, device=self.weight.device)
+        ops.copy_rows(self.weight, out, src_rows=ids32)
+        return out
+
+
+class _Linear:
+    """lm_head etc.: callable like nn.Linear (bf16 in/out), runs bagel_gemm_bf16."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        self.weight, self.bias = weight, bias
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        shp = x.shape
+        y = ops.gemm(x.reshape(-1, shp[-1]).to(BF16).contiguous(), self.weight, bias=self.bias)
+        return y.reshape(*shp[:-1], self.weight.shape[0])
+
+
+class _ExpertWeights:
+    """One expert's ("" = und, "_moe_gen" = gen) weights of one decoder layer, in kernel layouts."""
+    __slots__ = ("wqkv", "bqkv", "wo", "wgu", "wd", "ln_in", "ln_post", "q_norm", "k_norm")
+
+
+class _Layer:
+    def __init__(self):
+        self.und = _ExpertWeights()
+        self.gen: Optional[_ExpertWeights] = None
+
+
+class ForwardPlan:
+    """Everything about one packed LM call that does not depend on the hidden states: int32 index maps on the
+    device, cu_seqlens, RoPE tables. Built once per call (or once per denoising run) so the layer loop is pure
+    kernel launches with no host<->device synchronisation (the reference syncs >= 2x per layer, :585-586)."""
+
+    def __init__(self, lm: "Qwen2Model", query_lens, position_ids, packed_query_indexes, key_values_lens,
+                 packed_key_value_indexes, is_causal: bool, mode: str, packed_vae_token_indexes=None,
+                 packed_text_indexes=None):
+        dev = lm.device
+        cfg = lm.config
+        ql = torch.as_tensor(query_lens).to("cpu", torch.int64).reshape(-1)
+        self.batch = int(ql.numel())
+        self.n = int(ql.sum())
+        if key_values_lens is None:
+            kl = torch.zeros_like(ql)
+        else:
+            kl = torch.as_tensor(key_values_lens).to("cpu", torch.int64).reshape(-1)
+        self.n_ctx = int(kl.sum())
+        self.total_kv = self.n + self.n_ctx
+        tot = kl + ql
+        self.max_q = int(ql.max()) if self.batch else 0
+        self.max_k = int(tot.max()) if self.batch else 0
+        z = torch.zeros(1, dtype=torch.int64)
+        self.cu_q = torch.cat([z, ql.cumsum(0)]).to(dev, torch.int32)
+        self.cu_k = torch.cat([z, tot.cumsum(0)]).to(dev, torch.int32)
+        self.is_causal = bool(is_causal)
+        self.mode = mode
+        self.fp32_flow = (mode == "gen")
+        self.q_rows = torch.as_tensor(packed_query_indexes).to(dev, torch.int32).contiguous()
+        if self.n_ctx:
+            self.ctx_rows = torch.as_tensor(packed_key_value_indexes).to(dev, torch.int32).contiguous()
+        else:
+            self.ctx_rows = None
+        self.expert = None
+        self.text_rows = None
+        if mode == "gen" and lm.use_moe:
+            ex = torch.zeros(self.n, dtype=torch.uint8)
+            vi = torch.as_tensor(packed_vae_token_indexes).to("cpu", torch.int64)
+            ex[vi] = 1
+            self.expert = ex.to(dev)
+            ti = torch.as_tensor(packed_text_indexes).to("cpu", torch.int64)
+            self.text_rows = ti.to(dev, torch.int32).contiguous() if ti.numel() else None
+        pos = torch.as_tensor(position_ids).to(dev, torch.int64).contiguous()
+        assert pos.numel() == self.n, "one position id per packed query token"
+        # cos/sin take the dtype of the hidden stream (bf16 in mode A): modeling_qwen2.py:150
+        self.cos, self.sin = ops.rope_table(pos, lm.inv_freq, round_bf16=True)
+
+
+class Qwen2Model:
+    """The decoder stack (reference Qwen2Model, qwen2_navit.py:943-1092)."""
+
+    def __init__(self, config: Qwen2Config, device="cuda"):
+        self.config = config
+        self.device = torch.device(device)
+        self.use_moe = "Mo" in config.layer_module
+        self.enable_taylorseer = False
+        self.layers: List[_Layer] = [_Layer() for _ in range(config.num_hidden_layers)]
+        self.embed_tokens: Optional[_Embedding] = None
+        self.norm = None
+        self.norm_moe_gen = None
+        d = config.head_dim
+        # same expression as the reference's default rope init (fp32), computed on the host then moved
+        self.inv_freq = (1.0 / (config.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(self.device)
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    # ----------------------------------------------------------------------------------------------
+    def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        """Grow-only activation workspace (no allocation inside the layer loop once warmed up)."""
+        t = self._ws.get(name)
+        if t is None or t.shape[0] < rows or t.shape[1] != cols:
+            t = torch.empty((rows, cols), dtype=BF16, device=self.device)
+            self._ws[name] = t
+        return t[:rows]
+
+    def make_plan(self, **kw) -> ForwardPlan:
+        return ForwardPlan(self, **kw)
+
+    def alloc_kv(self, plan: ForwardPlan):
+        """Merged K/V buffers [total_kv, Hk*D] for every layer (the reference re-allocates these per layer per
+        call, qwen2_navit.py:563-569)."""
+        cfg = self.config
+        w = cfg.num_key_value_heads * cfg.head_dim
+        L = cfg.num_hidden_layers
+        k = torch.empty((L, plan.total_kv, w), dtype=BF16, device=self.device)
+        v = torch.empty((L, plan.total_kv, w), dtype=BF16, device=self.device)
+        return k, v
+
+    def place_context(self, plan: ForwardPlan, cache: Optional[NaiveCache], kbuf, vbuf):
+        """Copy the cached K/V rows to their slots in the merged buffers (reference :565-569)."""
+        if not plan.n_ctx:
+            return
+        cfg = self.config
+        w = cfg.num_key_value_heads * cfg.head_dim
+        for li in range(cfg.num_hidden_layers):
+            pk, pv = cache.key_cache[li], cache.value_cache[li]
+            assert pk is not None and pk.shape[0] == plan.n_ctx, "cache rows must match key_values_lens"
+            ops.copy_rows(pk.reshape(plan.n_ctx, w), kbuf[li], dst_rows=plan.ctx_rows, M=plan.n_ctx)
+            ops.copy_rows(pv.reshape(plan.n_ctx, w), vbuf[li], dst_rows=plan.ctx_rows, M=plan.n_ctx)
+
+    # ----------------------------------------------------------------------------------------------
+    def run_layers(self, x: torch.Tensor, plan: ForwardPlan, kbuf: torch.Tensor, vbuf: torch.Tensor) -> torch.Tensor:
+        """All decoder layers + final norm on a packed bf16 sequence x [n, H]. kbuf/vbuf: [L, total_kv, Hk*D]
+        with the context rows already in place; the new K/V rows are written by the qk-norm/RoPE kernel.
+        Pure kernel launches (CUDA-graph capturable)."""
+        cfg = self.config
+        n, H = plan.n, cfg.hidden_size
+        Hq, Hk, D, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
+        eps = cfg.rms_norm_eps
+        routed = plan.expert is not None
+        nt = plan.text_rows.numel() if (routed and plan.text_rows is not None) else 0
+
+        xa = self._buf("xa", n, H)
+        xb = self._buf("xb", n, H)
+        h = self._buf("h", n, H)
+        qkv = self._buf("qkv", n, (Hq + 2 * Hk) * D)
+        q = self._buf("q", n, Hq * D)
+        att = self._buf("att", n, Hq * D)
+        act = self._buf("act", n, I)
+        if nt:
+            ht = self._buf("h_text", nt, H)
+            at = self._buf("att_text", nt, Hq * D)
+            actt = self._buf("act_text", nt, I)
+        if x.data_ptr() != xa.data_ptr():
+            xa.copy_(x)
+
+        for li, layer in enumerate(self.layers):
+            main = layer.gen if routed else layer.und
+            und = layer.und
+            # ---- attention block ----
+            ops.rmsnorm(xa, und.ln_in, main.ln_in if routed else None, plan.expert, eps, out=h)
+            ops.gemm(h, main.wqkv, bias=main.bqkv, out=qkv)
+            if nt:
+                ops.copy_rows(h, ht, src_rows=plan.text_rows)
+                ops.gemm(ht, und.wqkv, bias=und.bqkv, row_map=plan.text_rows, out=qkv)
+            ops.qk_norm_rope(qkv, und.q_norm, und.k_norm, main.q_norm if routed else None,
+                             main.k_norm if routed else None, plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li],
+                             plan.q_rows, Hq, Hk, D, eps, plan.fp32_flow)
+            ops.attn_varlen(q.view(n, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), plan.cu_q, plan.cu_k,
+                            plan.max_q, plan.max_k, plan.is_causal, out=att.view(n, Hq, D))
+            ops.gemm(att, main.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
+            if nt:
+                ops.copy_rows(att, at, src_rows=plan.text_rows)
+                ops.gemm(at, und.wo, resid=xa, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xb)
+            # ---- MLP block ----
+            ops.rmsnorm(xb, und.ln_post, main.ln_post if routed else None, plan.expert, eps, out=h)
+            ops.gemm(h, main.wgu, epilogue=ops.EPI_SWIGLU, out=act)
+            ops.gemm(act, main.wd, resid=xb, epilogue=ops.EPI_RESID, out=xa)
+            if nt:
+                ops.copy_rows(h, ht, src_rows=plan.text_rows)
+                ops.gemm(ht, und.wgu, epilogue=ops.EPI_SWIGLU, out=actt)
+                ops.gemm(actt, und.wd, resid=xb, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xa)
+
+        out = self._buf("out", n, H)
+        ops.rmsnorm(xa, self.norm, self.norm_moe_gen if routed else None, plan.expert, eps, out=out)
+        return out
+
+    # ----------------------------------------------------------------------------------------------
+    def forward_inference(self, packed_query_sequence, query_lens, packed_query_position_ids, packed_query_indexes,
+                          past_key_values: Optional[NaiveCache] = None, key_values_lens=None,
+                          packed_key_value_indexes=None, update_past_key_values=True, is_causal=True, mode="und",
+                          packed_vae_token_indexes=None, packed_text_indexes=None) -> BaseNavitOutputWithPast:
+        if self.enable_taylorseer:
+            raise NotImplementedError("TaylorSeer step caching is out of scope (SURVEY.md §8f #1)")
+        if not self.use_moe:
+            mode = "und"
+        has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None
+        plan = ForwardPlan(self, query_lens, packed_query_position_ids, packed_query_indexes,
+                           key_values_lens if has_ctx else None, packed_key_value_indexes if has_ctx else None,
+                           is_causal, mode, packed_vae_token_indexes, packed_text_indexes)
+        x = packed_query_sequence.to(self.device, BF16)
+        kbuf, vbuf = self.alloc_kv(plan)
+        self.place_context(plan, past_key_values, kbuf, vbuf)
+        out = self.run_layers(x, plan, kbuf, vbuf).clone()
+        if update_past_key_values:
+            cfg = self.config
+            for li in range(cfg.num_hidden_layers):
+                past_key_values.key_cache[li] = kbuf[li].view(-1, cfg.num_key_value_heads, cfg.head_dim)
+                past_key_values.value_cache[li] = vbuf[li].view(-1, cfg.num_key_value_heads, cfg.head_dim)
+        return BaseNavitOutputWithPast(packed_query_sequence=out, past_key_values=past_key_values)
+
+    __call__ = forward_inference
+
+
+class Qwen2ForCausalLM:
+    """Reference Qwen2ForCausalLM (qwen2_navit.py:1095-1188): `.model`, `.lm_head`, forward_inference(...)."""
+
+    def __init__(self, config: Qwen2Config, device="cuda"):
+        self.config = config
+        self.model = Qwen2Model(config, device)
+        self.lm_head: Optional[_Linear] = None
+        self.vocab_size = config.vocab_size
+
+    @property
+    def device(self):
+        return self.model.device
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        """`sd` uses the reference's parameter names: model.layers.{i}.self_attn.q_proj.weight ...
+        Builds the fused kernel layouts on the device."""
+        cfg = self.config
+        dev = self.model.device
+        used = set()
+
+        def get(name, required=True):
+            if name in sd:
+                used.add(name)
+                return sd[name].to(dev, BF16)
+            if required:
+                raise KeyError(f"missing weight {name}")
+            return None
+
+        self.model.embed_tokens = _Embedding(get("model.embed_tokens.weight").contiguous())
+        for li, layer in enumerate(self.model.layers):
+            p = f"model.layers.{li}."
+            for sfx, tgt in (("", "und"), ("_moe_gen", "gen")):
+                if sfx and not self.model.use_moe:
+                    continue
+                e = _ExpertWeights()
+                a = p + "self_attn."
+                e.wqkv = torch.cat([get(a + f"q_proj{sfx}.weight"), get(a + f"k_proj{sfx}.weight"),
+                                    get(a + f"v_proj{sfx}.weight")], dim=0).contiguous()
+                e.bqkv = torch.cat([get(a + f"q_proj{sfx}.bias"), get(a + f"k_proj{sfx}.bias"),
+                                    get(a + f"v_proj{sfx}.bias")], dim=0).contiguous()
+                e.wo = get(a + f"o_proj{sfx}.weight").contiguous()
+                if cfg.qk_norm:
+                    e.q_norm = get(a + f"q_norm{sfx}.weight").contiguous()
+                    e.k_norm = get(a + f"k_norm{sfx}.weight").contiguous()
+                else:
+                    raise NotImplementedError("qk_norm=False is not used by any shipped BAGEL config")
+                m = p + f"mlp{sfx}."
+                e.wgu = ops.interleave_gate_up(get(m + "gate_proj.weight"), get(m + "up_proj.weight"))
+                e.wd = get(m + "down_proj.weight").contiguous()
+                e.ln_in = get(p + f"input_layernorm{sfx}.weight").contiguous()
+                e.ln_post = get(p + f"post_attention_layernorm{sfx}.weight").contiguous()
+                setattr(layer, tgt, e)
+        self.model.norm = get("model.norm.weight").contiguous()
+        if self.model.use_moe:
+            self.model.norm_moe_gen = get("model.norm_moe_gen.weight").contiguous()
+        lw = get("lm_head.weight", required=False)
+        if lw is None and cfg.tie_word_embeddings:
+            lw = self.model.embed_tokens.weight
+        self.lm_head = _Linear(lw.contiguous()) if lw is not None else None
+        unexpected = [k for k in sd if k not in used]
+        if strict and unexpected:
+            raise KeyError(f"unexpected keys: {unexpected[:8]}")
+        return unexpected
+
+    def forward_inference(self, *args, **kwargs) -> BaseNavitOutputWithPast:
+        return self.model.forward_inference(*args, **kwargs)
+
+    __call__ = forward_inference

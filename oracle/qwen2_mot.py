@@ -15,6 +15,19 @@ import torch
 import torch.nn.functional as F
 
 BF16 = torch.bfloat16
+_AUTOCAST = [torch.bfloat16]  # dtype nn.Linear / attention run in; see high_precision()
+
+
+class high_precision:
+    """Context manager: run the same graph in fp32 end to end (fp32 weights expected) — the "exact" answer the
+    bf16 pipelines (reference and GPU build) both approximate. Used by the parity tests to express tolerances
+    as "no further from the truth than the reference itself"."""
+
+    def __enter__(self):
+        _AUTOCAST[0] = torch.float32
+
+    def __exit__(self, *a):
+        _AUTOCAST[0] = torch.bfloat16
 
 
 @dataclass
@@ -35,7 +48,8 @@ class LMConfig:
 
 def linear(x, w, b=None):
     """nn.Linear under autocast(bf16): operands cast to bf16, bf16 result."""
-    return F.linear(x.to(BF16), w.to(BF16), None if b is None else b.to(BF16))
+    dt = _AUTOCAST[0]
+    return F.linear(x.to(dt), w.to(dt), None if b is None else b.to(dt))
 
 
 def rms_norm(x, w, eps):
@@ -117,7 +131,7 @@ def _attention(x, sd, cfg: LMConfig, li: int, cos, sin, query_lens, packed_query
         q = rms_norm(q, sd[p + "q_norm.weight"], eps)
         k = rms_norm(k, sd[p + "k_norm.weight"], eps)
     else:
-        x = x.to(BF16)
+        x = x.to(_AUTOCAST[0])
         n = x.shape[0]
         q = x.new_zeros((n, Hq * d))
         k = x.new_zeros((n, Hk * d))
@@ -135,7 +149,7 @@ def _attention(x, sd, cfg: LMConfig, li: int, cos, sin, query_lens, packed_query
         k[vae_idx] = rms_norm(k[vae_idx], sd[p + "k_norm_moe_gen.weight"], eps)
 
     q, k = apply_rope(q, k, cos, sin)
-    q, k, v = q.to(BF16), k.to(BF16), v.to(BF16)
+    q, k, v = q.to(_AUTOCAST[0]), k.to(_AUTOCAST[0]), v.to(_AUTOCAST[0])
 
     if cache is not None and cache.key_cache[li] is not None:
         pk, pv = cache.key_cache[li], cache.value_cache[li]
@@ -180,9 +194,9 @@ def _layer(x, sd, cfg, li, cos, sin, mode, vae_idx, text_idx, **attn_kw):
         h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], eps)
         m = swiglu_mlp(h, sd, p + "mlp.")
     else:
-        ht = rms_norm(x[text_idx], sd[p + "post_attention_layernorm.weight"], eps).to(BF16)
-        hv = rms_norm(x[vae_idx], sd[p + "post_attention_layernorm_moe_gen.weight"], eps).to(BF16)
-        m = torch.zeros_like(x).to(BF16)
+        ht = rms_norm(x[text_idx], sd[p + "post_attention_layernorm.weight"], eps).to(_AUTOCAST[0])
+        hv = rms_norm(x[vae_idx], sd[p + "post_attention_layernorm_moe_gen.weight"], eps).to(_AUTOCAST[0])
+        m = torch.zeros_like(x).to(_AUTOCAST[0])
         m[text_idx] = swiglu_mlp(ht, sd, p + "mlp.")
         m[vae_idx] = swiglu_mlp(hv, sd, p + "mlp_moe_gen.")
     return resid + m

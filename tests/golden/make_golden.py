@@ -1,0 +1,220 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no reference tree):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.safetensors. The reference ships no tests / golden vectors, so these are
+the pins: every tensor below is produced by the reference's own classes (with the harness shims of
+oracle/ref_shims.py), from the deterministic synthetic weights/inputs of oracle/fixtures.py. While generating,
+the script also asserts that the oracle restatement reproduces the reference bit-for-bit.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from types import SimpleNamespace
+
+import torch
+from safetensors.torch import save_file
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import bagel_flow as obf  # noqa: E402
+from oracle import fixtures, qwen2_mot as om, ref_shims  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+NEW_TOKEN_IDS = dict(bos_token_id=1000, eos_token_id=1001, start_of_image=1002, end_of_image=1003)
+
+
+class IntTokenizer:
+    """Prompts are strings of space-separated token ids (no vocab files offline)."""
+
+    def encode(self, prompt):
+        return [int(t) for t in prompt.split()]
+
+
+def ref_lm(ns, cfg, sd, dtype):
+    rcfg = ref_shims.make_llm_config(
+        ns, vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta, max_position_embeddings=32768)
+    lm = ref_shims.cast_parameters(ns.qwen2_navit.Qwen2ForCausalLM(rcfg).eval(), dtype)
+    lm.load_state_dict(sd, strict=True)
+    return lm, rcfg
+
+
+def golden_lm_config1(ns):
+    """BASELINE configs[0]: 2-layer / 256-dim MoT forward, seq 512, batch 1 (und prefill, then gen on top)."""
+    out = {}
+    for tag, cfg in (("d64", fixtures.TINY_LM), ("d128", fixtures.TINY128_LM)):
+        for mode, dtype in (("A", torch.bfloat16), ("B", torch.float32)):
+            if tag == "d128" and mode == "B":
+                continue
+            sd = fixtures.lm_state_dict(cfg, seed=0, dtype=dtype)
+            lm, _ = ref_lm(ns, cfg, sd, dtype)
+            inp = fixtures.config1_inputs(cfg, dtype=dtype)
+            n = 130
+            xg = torch.randn(n, cfg.hidden_size, generator=torch.Generator().manual_seed(5)).to(dtype)
+            kw = dict(query_lens=torch.tensor([n], dtype=torch.int32),
+                      packed_query_position_ids=torch.full((n,), 512, dtype=torch.long),
+                      packed_query_indexes=torch.arange(512, 512 + n),
+                      key_values_lens=torch.tensor([512], dtype=torch.int32),
+                      packed_key_value_indexes=torch.arange(512), update_past_key_values=False, is_causal=False,
+                      mode="gen", packed_vae_token_indexes=torch.arange(1, n - 1),
+                      packed_text_indexes=torch.tensor([0, n - 1]))
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                cache = ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers)
+                und = lm.forward_inference(
+                    packed_query_sequence=inp["x"], query_lens=inp["query_lens"],
+                    packed_query_position_ids=inp["und_position_ids"], packed_query_indexes=inp["query_indexes"],
+                    past_key_values=cache, key_values_lens=torch.tensor([0], dtype=torch.int32),
+                    packed_key_value_indexes=torch.zeros(0, dtype=torch.long), update_past_key_values=True,
+                    is_causal=True, mode="und")
+                gen = lm.forward_inference(packed_query_sequence=xg, past_key_values=cache, **kw)
+            with torch.no_grad():
+                oc = om.KVCache(cfg.num_hidden_layers)
+                oh, oc = om.lm_forward_inference(sd, cfg, inp["x"], inp["query_lens"], inp["und_position_ids"],
+                                                 inp["query_indexes"], oc, torch.tensor([0], dtype=torch.int32),
+                                                 torch.zeros(0, dtype=torch.long), True, True, "und")
+                og, _ = om.lm_forward_inference(sd, cfg, xg, past_key_values=oc, **kw)
+            assert torch.equal(oh, und.packed_query_sequence) and torch.equal(og, gen.packed_query_sequence), \
+                f"oracle != reference ({tag}, mode {mode})"
+            for li in range(cfg.num_hidden_layers):
+                assert torch.equal(oc.key_cache[li], cache.key_cache[li])
+            pre = f"{tag}.{mode}."
+            out[pre + "und_hidden"] = und.packed_query_sequence.contiguous()
+            out[pre + "gen_hidden"] = gen.packed_query_sequence.contiguous()
+            out[pre + "k_cache_last"] = cache.key_cache[cfg.num_hidden_layers - 1].contiguous()
+            out[pre + "v_cache_last"] = cache.value_cache[cfg.num_hidden_layers - 1].contiguous()
+            print(f"lm_config1 {tag} mode {mode}: oracle == reference (bit-exact)")
+    save_file(out, os.path.join(OUT, "lm_config1.safetensors"))
+
+
+def build_ref_bagel(ns, cfg, sd_all, dtype, max_latent_size=8):
+    lm_sd = {k[len("language_model."):]: v for k, v in sd_all.items() if k.startswith("language_model.")}
+    lm, rcfg = ref_lm(ns, cfg, lm_sd, dtype)
+    vae_cfg = SimpleNamespace(downsample=8, z_channels=16)
+    bcfg = ns.bagel.BagelConfig(visual_gen=True, visual_und=False, llm_config=rcfg, vit_config=None,
+                                vae_config=vae_cfg, latent_patch_size=2, max_latent_size=max_latent_size)
+    model = ns.bagel.Bagel(lm, None, bcfg).eval()
+    ref_shims.cast_parameters(model, dtype)
+    missing = model.load_state_dict(sd_all, strict=False)
+    assert not missing.unexpected_keys, missing
+    assert all("pos_embed" in k for k in missing.missing_keys), missing
+    return model
+
+
+def flow_state_dict(cfg, dtype, max_latent_size=8):
+    sd = {"language_model." + k: v for k, v in fixtures.lm_state_dict(cfg, seed=0, dtype=dtype).items()}
+    sd.update(fixtures.bagel_extra_state_dict(cfg.hidden_size, seed=1, dtype=dtype))
+    return sd
+
+
+def golden_flow(ns):
+    """Packers + text prefill + generate_image (4 timesteps = 3 evals, B=2 ragged images, CFG variants)."""
+    cfg = fixtures.TINY_LM
+    dtype = torch.bfloat16
+    sd = flow_state_dict(cfg, dtype)
+    model = build_ref_bagel(ns, cfg, sd, dtype)
+    sd_full = dict(sd)
+    sd_full["latent_pos_embed.pos_embed"] = model.latent_pos_embed.pos_embed.data.clone()
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    assert torch.equal(obf.sincos_2d_table(cfg.hidden_size, 8).to(dtype), sd_full["latent_pos_embed.pos_embed"])
+    tok = IntTokenizer()
+    prompts = ["5 17 900 33 2", "8 8 100 4 77 650 12"]
+    prompt_ids = [tok.encode(p) for p in prompts]
+    image_sizes = [(64, 64), (64, 96)]
+    out = {}
+
+    def ctx(with_text):
+        """(cache, kv_lens, ropes) for the reference and the oracle."""
+        rc = ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers)
+        oc = om.KVCache(cfg.num_hidden_layers)
+        kv, rp = [0, 0], [0, 0]
+        if with_text:
+            gi, kv2, rp2 = model.prepare_prompts(kv, rp, prompts, tok, NEW_TOKEN_IDS)
+            ogi, okv, orp = obf.prepare_prompts(kv, rp, prompt_ids, NEW_TOKEN_IDS["bos_token_id"],
+                                                NEW_TOKEN_IDS["eos_token_id"])
+            assert kv2 == okv and rp2 == orp
+            for k in gi:
+                assert torch.equal(gi[k], ogi[k]) and gi[k].dtype == ogi[k].dtype, k
+                out["prompts." + k] = gi[k].clone()
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                rc = model.forward_cache_update_text(rc, **gi)
+            with torch.no_grad():
+                oc = obf.forward_cache_update_text(sd_full, fc, oc, **ogi)
+            for li in range(cfg.num_hidden_layers):
+                assert torch.equal(rc.key_cache[li], oc.key_cache[li])
+            kv, rp = kv2, rp2
+        return rc, oc, kv, rp
+
+    rc_main, oc_main, kv_main, rp_main = ctx(True)
+    rc_txt, oc_txt, kv_txt, rp_txt = ctx(False)      # text-dropped branch: empty context
+    rc_img, oc_img, kv_img, rp_img = ctx(True)       # "image-dropped" branch of a T2I call = text only
+    out["prefill.k_cache_last"] = rc_main.key_cache[cfg.num_hidden_layers - 1].contiguous()
+    out["prefill.kv_lens"] = torch.tensor(kv_main)
+    out["prefill.ropes"] = torch.tensor(rp_main)
+
+    torch.manual_seed(2)
+    gi = model.prepare_vae_latent(kv_main, rp_main, image_sizes, NEW_TOKEN_IDS)
+    torch.manual_seed(2)
+    ogi = obf.prepare_vae_latent(fc, kv_main, rp_main, image_sizes, NEW_TOKEN_IDS["start_of_image"],
+                                 NEW_TOKEN_IDS["end_of_image"])
+    for k in gi:
+        assert torch.equal(gi[k], ogi[k]) and gi[k].dtype == ogi[k].dtype, k
+        out["latent." + k] = gi[k].clone()
+    cfg_t = model.prepare_vae_latent_cfg(kv_txt, rp_txt, image_sizes)
+    cfg_i = model.prepare_vae_latent_cfg(kv_img, rp_img, image_sizes)
+    ocfg_t = obf.prepare_vae_latent_cfg(fc, kv_txt, rp_txt, image_sizes)
+    for k in cfg_t:
+        assert torch.equal(cfg_t[k], ocfg_t[k]), k
+        out["cfg_text." + k] = cfg_t[k].clone()
+        out["cfg_img." + k] = cfg_i[k].clone()
+
+    def obranch(d, cache):
+        return dict(packed_position_ids=d["cfg_packed_position_ids"], packed_query_indexes=d["cfg_packed_query_indexes"],
+                    key_values_lens=d["cfg_key_values_lens"], past_key_values=cache,
+                    packed_key_value_indexes=d["cfg_packed_key_value_indexes"])
+
+    variants = [("nocfg", 1.0, 1.0, "global"), ("global", 4.0, 1.0, "global"), ("channel", 4.0, 1.0, "channel"),
+                ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel")]
+    for name, sT, sI, rt in variants:
+        kwargs = dict(num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type=rt,
+                      cfg_interval=[0.4, 1.0], cfg_text_scale=sT, cfg_img_scale=sI)
+        ref_kw = dict(kwargs)
+        ref_kw.update(
+            cfg_text_packed_position_ids=cfg_t["cfg_packed_position_ids"],
+            cfg_text_packed_query_indexes=cfg_t["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=cfg_t["cfg_key_values_lens"],
+            cfg_text_packed_key_value_indexes=cfg_t["cfg_packed_key_value_indexes"],
+            cfg_text_past_key_values=rc_txt,
+            cfg_img_packed_position_ids=cfg_i["cfg_packed_position_ids"],
+            cfg_img_packed_query_indexes=cfg_i["cfg_packed_query_indexes"],
+            cfg_img_key_values_lens=cfg_i["cfg_key_values_lens"],
+            cfg_img_packed_key_value_indexes=cfg_i["cfg_packed_key_value_indexes"],
+            cfg_img_past_key_values=rc_img)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            lat = model.generate_image(past_key_values=rc_main, **gi, **ref_kw)
+        with torch.no_grad():
+            olat = obf.generate_image(sd_full, fc, ogi, oc_main, cfg_text=obranch(cfg_t, oc_txt),
+                                      cfg_img=obranch(cfg_i, oc_img), **kwargs)
+        for a, b in zip(lat, olat):
+            assert torch.equal(a, b), f"oracle generate_image != reference ({name})"
+        out[f"gen.{name}.latents"] = torch.cat(lat, dim=0).contiguous()
+        print(f"generate_image[{name}]: oracle == reference (bit-exact); |x| mean {float(torch.cat(lat).abs().mean()):.4f}")
+    save_file(out, os.path.join(OUT, "flow_tiny.safetensors"))
+
+
+def main():
+    if not ref_shims.reference_available():
+        raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
+    torch.set_num_threads(8)
+    ns = ref_shims.load_reference()
+    golden_lm_config1(ns)
+    golden_flow(ns)
+    sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
+    print("wrote", sizes)
+
+
+if __name__ == "__main__":
+    main()

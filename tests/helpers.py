@@ -1,0 +1,42 @@
+"""Shared builders for the tests: tiny synthetic BAGEL (weights from oracle/fixtures.py), int tokenizer."""
+from __future__ import annotations
+
+import torch
+
+from oracle import bagel_flow as obf
+from oracle import fixtures
+
+NEW_TOKEN_IDS = dict(bos_token_id=1000, eos_token_id=1001, start_of_image=1002, end_of_image=1003)
+PROMPTS = ["5 17 900 33 2", "8 8 100 4 77 650 12"]
+IMAGE_SIZES = [(64, 64), (64, 96)]
+
+
+class IntTokenizer:
+    def encode(self, prompt):
+        return [int(t) for t in prompt.split()]
+
+
+def flow_state_dict(cfg=fixtures.TINY_LM, dtype=torch.bfloat16, max_latent_size=8):
+    sd = {"language_model." + k: v for k, v in fixtures.lm_state_dict(cfg, seed=0, dtype=dtype).items()}
+    sd.update(fixtures.bagel_extra_state_dict(cfg.hidden_size, seed=1, dtype=dtype))
+    sd["latent_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, max_latent_size).to(dtype)
+    return sd
+
+
+def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, load=True):
+    """bagel_b200.Bagel for the tiny config (device='cpu' only exercises host logic: packers, config)."""
+    from bagel_b200.bagel import Bagel
+    from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config
+    from bagel_b200.qwen2_navit import Qwen2ForCausalLM
+
+    llm = Qwen2Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                      num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                      num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta,
+                      rms_norm_eps=cfg.rms_norm_eps, qk_norm=True, layer_module="Qwen2MoTDecoderLayer")
+    bcfg = BagelConfig(visual_gen=True, visual_und=False, llm_config=llm, vit_config=None,
+                       vae_config=AutoEncoderParams(), latent_patch_size=2, max_latent_size=max_latent_size)
+    lm = Qwen2ForCausalLM(llm, device=device)
+    model = Bagel(lm, None, bcfg)
+    if load:
+        model.load_state_dict(flow_state_dict(cfg, max_latent_size=max_latent_size))
+    return model

@@ -1,0 +1,111 @@
+"""The oracle (CPU restatement) must reproduce the committed reference outputs bit-for-bit.
+Fixtures: tests/golden/*.safetensors, generated from the unmodified reference by tests/golden/make_golden.py."""
+import os
+
+import pytest
+import torch
+from safetensors.torch import load_file
+
+import helpers
+from oracle import bagel_flow as obf
+from oracle import fixtures, qwen2_mot as om
+
+
+@pytest.fixture(scope="module")
+def g_lm(golden_dir):
+    return load_file(os.path.join(golden_dir, "lm_config1.safetensors"))
+
+
+@pytest.fixture(scope="module")
+def g_flow(golden_dir):
+    return load_file(os.path.join(golden_dir, "flow_tiny.safetensors"))
+
+
+@pytest.mark.parametrize("tag,cfg,mode,dtype", [
+    ("d64", fixtures.TINY_LM, "A", torch.bfloat16),
+    ("d64", fixtures.TINY_LM, "B", torch.float32),
+    ("d128", fixtures.TINY128_LM, "A", torch.bfloat16),
+])
+def test_lm_config1_bit_exact(g_lm, tag, cfg, mode, dtype):
+    """BASELINE configs[0]: 2-layer/256-dim MoT forward, seq 512, batch 1, CPU."""
+    sd = fixtures.lm_state_dict(cfg, seed=0, dtype=dtype)
+    inp = fixtures.config1_inputs(cfg, dtype=dtype)
+    with torch.no_grad():
+        cache = om.KVCache(cfg.num_hidden_layers)
+        h, cache = om.lm_forward_inference(sd, cfg, inp["x"], inp["query_lens"], inp["und_position_ids"],
+                                           inp["query_indexes"], cache, torch.tensor([0], dtype=torch.int32),
+                                           torch.zeros(0, dtype=torch.long), True, True, "und")
+        pre = f"{tag}.{mode}."
+        assert torch.equal(h, g_lm[pre + "und_hidden"])
+        last = cfg.num_hidden_layers - 1
+        assert torch.equal(cache.key_cache[last], g_lm[pre + "k_cache_last"])
+        assert torch.equal(cache.value_cache[last], g_lm[pre + "v_cache_last"])
+        n = 130
+        xg = torch.randn(n, cfg.hidden_size, generator=torch.Generator().manual_seed(5)).to(dtype)
+        hg, _ = om.lm_forward_inference(
+            sd, cfg, xg, torch.tensor([n], dtype=torch.int32), torch.full((n,), 512, dtype=torch.long),
+            torch.arange(512, 512 + n), cache, torch.tensor([512], dtype=torch.int32), torch.arange(512), False,
+            False, "gen", torch.arange(1, n - 1), torch.tensor([0, n - 1]))
+        assert torch.equal(hg, g_lm[pre + "gen_hidden"])
+
+
+def _oracle_contexts(sd, fc, cfg):
+    tok = helpers.IntTokenizer()
+    ids = [tok.encode(p) for p in helpers.PROMPTS]
+
+    def ctx(with_text):
+        c = om.KVCache(cfg.num_hidden_layers)
+        kv, rp = [0, 0], [0, 0]
+        gi = None
+        if with_text:
+            gi, kv, rp = obf.prepare_prompts(kv, rp, ids, helpers.NEW_TOKEN_IDS["bos_token_id"],
+                                             helpers.NEW_TOKEN_IDS["eos_token_id"])
+            c = obf.forward_cache_update_text(sd, fc, c, **gi)
+        return c, kv, rp, gi
+
+    return ctx
+
+
+def test_packers_and_prefill_bit_exact(g_flow):
+    cfg = fixtures.TINY_LM
+    sd = helpers.flow_state_dict(cfg)
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    with torch.no_grad():
+        c, kv, rp, gi = _oracle_contexts(sd, fc, cfg)(True)
+    for k, v in gi.items():
+        assert torch.equal(v, g_flow["prompts." + k]) and v.dtype == g_flow["prompts." + k].dtype, k
+    assert kv == g_flow["prefill.kv_lens"].tolist() and rp == g_flow["prefill.ropes"].tolist()
+    assert torch.equal(c.key_cache[cfg.num_hidden_layers - 1], g_flow["prefill.k_cache_last"])
+    torch.manual_seed(2)
+    lat = obf.prepare_vae_latent(fc, kv, rp, helpers.IMAGE_SIZES, helpers.NEW_TOKEN_IDS["start_of_image"],
+                                 helpers.NEW_TOKEN_IDS["end_of_image"])
+    for k, v in lat.items():
+        assert torch.equal(v, g_flow["latent." + k]) and v.dtype == g_flow["latent." + k].dtype, k
+
+
+@pytest.mark.parametrize("name,sT,sI,rt", [
+    ("nocfg", 1.0, 1.0, "global"), ("global", 4.0, 1.0, "global"), ("channel", 4.0, 1.0, "channel"),
+    ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel")])
+def test_generate_image_bit_exact(g_flow, name, sT, sI, rt):
+    cfg = fixtures.TINY_LM
+    sd = helpers.flow_state_dict(cfg)
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    with torch.no_grad():
+        ctx = _oracle_contexts(sd, fc, cfg)
+        c_main, kv_m, rp_m, _ = ctx(True)
+        c_txt, kv_t, rp_t, _ = ctx(False)
+        c_img, kv_i, rp_i, _ = ctx(True)
+        torch.manual_seed(2)
+        gi = obf.prepare_vae_latent(fc, kv_m, rp_m, helpers.IMAGE_SIZES, helpers.NEW_TOKEN_IDS["start_of_image"],
+                                    helpers.NEW_TOKEN_IDS["end_of_image"])
+
+        def br(kv, rp, cache):
+            d = obf.prepare_vae_latent_cfg(fc, kv, rp, helpers.IMAGE_SIZES)
+            return dict(packed_position_ids=d["cfg_packed_position_ids"],
+                        packed_query_indexes=d["cfg_packed_query_indexes"], key_values_lens=d["cfg_key_values_lens"],
+                        past_key_values=cache, packed_key_value_indexes=d["cfg_packed_key_value_indexes"])
+
+        lat = obf.generate_image(sd, fc, gi, c_main, num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0,
+                                 cfg_renorm_type=rt, cfg_interval=[0.4, 1.0], cfg_text_scale=sT,
+                                 cfg_text=br(kv_t, rp_t, c_txt), cfg_img_scale=sI, cfg_img=br(kv_i, rp_i, c_img))
+    assert torch.equal(torch.cat(lat, 0), g_flow[f"gen.{name}.latents"])
