@@ -366,6 +366,48 @@ class Bagel:
             runner.step(i)
         return runner.latents()
 
+    # ------------------------------------------------------------------------------------------
+    # text decode
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate_text(self, past_key_values: NaiveCache, packed_key_value_indexes, key_values_lens,
+                      packed_start_tokens, packed_query_position_ids, max_length: int, do_sample: bool = False,
+                      temperature: float = 1.0, end_token_id: Optional[int] = None):
+        """Greedy / sampled decode, one token per sample per step, KV appended (reference bagel.py:930-1000).
+        Returns [steps, B] token ids on the model's device. Like the reference, generation stops when SAMPLE 0
+        emits `end_token_id` (the reference supports batch 1 here, :996) and the stopping token is not returned.
+        Per-step index bookkeeping is done on the host in closed form (the reference rebuilds it with Python
+        loops over .tolist()); the LM call is the same packed `forward_inference(mode="und", is_causal=True)`."""
+        dev = self.device
+        kv = torch.as_tensor(key_values_lens).to("cpu", torch.int64)
+        B = int(kv.numel())
+        pos = torch.as_tensor(packed_query_position_ids).to("cpu", torch.int64).clone()
+        tokens = torch.as_tensor(packed_start_tokens).to(dev, torch.int64)
+        ones = torch.ones(B, dtype=torch.int32)
+        sample_ids = torch.arange(B, dtype=torch.int64)
+        out: List[torch.Tensor] = []
+        for _ in range(max_length):
+            out.append(tokens)
+            emb = self.language_model.model.embed_tokens(tokens)
+            # merged layout per sample: [cached_i | new token]; sample i starts at sum_{j<i}(kv_j + 1)
+            starts = torch.cumsum(kv + 1, 0) - (kv + 1)
+            res = self.language_model.forward_inference(
+                packed_query_sequence=emb, query_lens=ones, packed_query_position_ids=pos,
+                packed_query_indexes=starts + kv, past_key_values=past_key_values, key_values_lens=kv.to(torch.int32),
+                packed_key_value_indexes=_ranges(starts, kv), update_past_key_values=True, is_causal=True, mode="und")
+            past_key_values = res.past_key_values
+            logits = self.language_model.lm_head(res.packed_query_sequence)
+            if do_sample:
+                probs = torch.softmax(logits / temperature, dim=-1)
+                tokens = torch.multinomial(probs, num_samples=1).squeeze(1)
+            else:
+                tokens = torch.argmax(logits, dim=-1)
+            kv = kv + 1
+            pos = pos + 1
+            if end_token_id is not None and int(tokens[0]) == end_token_id:
+                break
+        return torch.stack(out, dim=0)
+
     @torch.no_grad()
     def _forward_flow(self, x_t, timestep, packed_vae_token_indexes, packed_vae_position_ids, packed_text_ids,
                       packed_text_indexes, packed_indexes, packed_position_ids, packed_seqlens, key_values_lens,

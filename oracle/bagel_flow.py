@@ -242,3 +242,47 @@ def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_tim
             trace.append(v.clone())
         x_t = x_t - v * dts[i]
     return x_t.split((gen_input["packed_seqlens"] - 2).tolist())
+
+
+def prepare_start_tokens(curr_kvlens, curr_rope, bos):
+    """bagel.py:909-927"""
+    kv_idx, cur = [], 0
+    for kvlen in curr_kvlens:
+        kv_idx += list(range(cur, cur + kvlen))
+        cur += kvlen
+    return {
+        "packed_start_tokens": torch.tensor([bos] * len(curr_kvlens), dtype=torch.long),
+        "packed_query_position_ids": torch.tensor(list(curr_rope), dtype=torch.long),
+        "key_values_lens": torch.tensor(curr_kvlens, dtype=torch.int),
+        "packed_key_value_indexes": torch.tensor(kv_idx, dtype=torch.long),
+    }
+
+
+def generate_text(sd, fc: FlowConfig, past_key_values, packed_key_value_indexes, key_values_lens,
+                  packed_start_tokens, packed_query_position_ids, max_length, end_token_id=None,
+                  logits_trace: Optional[list] = None):
+    """Greedy branch of bagel.py:930-1000 (do_sample=False). Returns [steps, B] ids."""
+    lsd = lm_sub(sd)
+    seq, cur = [], packed_start_tokens
+    kv = key_values_lens.clone()
+    pos = packed_query_position_ids.clone()
+    kv_idx = packed_key_value_indexes.clone()
+    for _ in range(max_length):
+        seq.append(cur)
+        emb = F.embedding(cur, sd["language_model.model.embed_tokens.weight"])
+        q_idx = torch.cumsum(kv, dim=0) + torch.arange(0, len(kv), dtype=kv.dtype)
+        parts = list(kv_idx.split(kv.tolist(), dim=0))
+        kv_idx = torch.cat([p + i for i, p in enumerate(parts)], dim=0)
+        h, past_key_values = om.lm_forward_inference(lsd, fc.lm, emb, torch.ones_like(cur), pos, q_idx, past_key_values,
+                                                     kv, kv_idx, True, True, "und")
+        logits = linear(h, sd["language_model.lm_head.weight"])
+        if logits_trace is not None:
+            logits_trace.append(logits.clone())
+        cur = torch.argmax(logits, dim=-1)
+        parts = list(kv_idx.split(kv.tolist(), dim=0))
+        kv_idx = torch.cat([torch.cat([p, p[-1:] + 1]) for p in parts], dim=0)
+        kv = kv + 1
+        pos = pos + 1
+        if end_token_id is not None and cur[0] == end_token_id:
+            break
+    return torch.stack(seq, dim=0)

@@ -202,6 +202,24 @@ def golden_flow(ns):
             assert torch.equal(a, b), f"oracle generate_image != reference ({name})"
         out[f"gen.{name}.latents"] = torch.cat(lat, dim=0).contiguous()
         print(f"generate_image[{name}]: oracle == reference (bit-exact); |x| mean {float(torch.cat(lat).abs().mean()):.4f}")
+    # ---- greedy text decode on top of the text context (bagel.py:930-1000), 12 steps, B=2 ----
+    from copy import deepcopy
+    gs = model.prepare_start_tokens(kv_main, rp_main, NEW_TOKEN_IDS)
+    ogs = obf.prepare_start_tokens(kv_main, rp_main, NEW_TOKEN_IDS["bos_token_id"])
+    for k in gs:
+        assert torch.equal(gs[k], ogs[k]) and gs[k].dtype == ogs[k].dtype, k
+        out["start." + k] = gs[k].clone()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        toks = model.generate_text(past_key_values=deepcopy(rc_main), max_length=12, do_sample=False, **gs)
+    trace = []
+    with torch.no_grad():
+        otoks = obf.generate_text(sd_full, fc, deepcopy(oc_main), max_length=12, logits_trace=trace, **ogs)
+    assert torch.equal(toks, otoks), "oracle generate_text != reference"
+    out["text.tokens"] = toks.contiguous()
+    out["text.logits"] = torch.stack(trace, 0).contiguous()      # [steps, B, vocab] bf16 (oracle == reference path)
+    top2 = torch.stack(trace, 0).float().topk(2, dim=-1).values
+    print("generate_text: oracle == reference (bit-exact); tokens", toks[:, 0].tolist(),
+          "min top-1/top-2 logit margin", float((top2[..., 0] - top2[..., 1]).min()))
     save_file(out, os.path.join(OUT, "flow_tiny.safetensors"))
 
 

@@ -220,3 +220,44 @@ def test_kv_cache_survives_deepcopy_and_context_is_not_mutated():
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_generate_text_greedy(g_flow):
+    """Text decode (bagel.py:930-1000). Token ids must be bit-exact wherever the reference's own top-1/top-2 logit
+    margin exceeds bf16 noise; the fixture holds the reference's logits so the first divergence (if any) is
+    attributed: a random-init model has near-uniform logits (min margin in the fixture: 1 bf16 ulp)."""
+    from copy import deepcopy
+    cfg = fixtures.TINY_LM
+    model = helpers.build_product_bagel(cfg, "cuda")
+    c_main, kv_m, rp_m = _contexts(model, cfg)(True)
+    gs = model.prepare_start_tokens(kv_m, rp_m, helpers.NEW_TOKEN_IDS)
+    for k in gs:
+        assert torch.equal(gs[k], g_flow["start." + k]), k
+    toks = model.generate_text(past_key_values=deepcopy(c_main), max_length=12, do_sample=False, **gs).cpu()
+    ref = g_flow["text.tokens"]
+    ref_logits = g_flow["text.logits"].float()               # [steps, B, V]
+    assert toks.shape == ref.shape and toks.dtype == torch.int64
+    assert torch.equal(toks[0], ref[0])
+    top2 = ref_logits.topk(2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]                      # [steps, B]
+    for b in range(ref.shape[1]):
+        for s in range(1, ref.shape[0]):
+            if toks[s, b] != ref[s, b]:
+                # tokens diverge only where the reference's decision at step s-1 was within bf16 noise
+                assert margin[s - 1, b] <= 0.07, f"sample {b} diverged at step {s} with margin {margin[s-1, b]:.4f}"
+                break
+    # teacher-forced: with the reference's token prefix, logits must agree to bf16 accuracy at every step
+    from bagel_b200.bagel import _ranges
+    cache = deepcopy(c_main)
+    kv = torch.tensor(kv_m, dtype=torch.int64)
+    pos = torch.tensor(rp_m, dtype=torch.int64)
+    for s in range(ref.shape[0]):
+        emb = model.language_model.model.embed_tokens(ref[s])
+        starts = torch.cumsum(kv + 1, 0) - (kv + 1)
+        out = model.language_model.forward_inference(
+            packed_query_sequence=emb, query_lens=torch.ones(2, dtype=torch.int32), packed_query_position_ids=pos,
+            packed_query_indexes=starts + kv, past_key_values=cache, key_values_lens=kv.to(torch.int32),
+            packed_key_value_indexes=_ranges(starts, kv), update_past_key_values=True, is_causal=True, mode="und")
+        logits = model.language_model.lm_head(out.packed_query_sequence).float().cpu()
+        torch.testing.assert_close(logits, ref_logits[s], atol=0.06, rtol=0.02)
+        kv, pos = kv + 1, pos + 1

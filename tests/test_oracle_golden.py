@@ -109,3 +109,20 @@ def test_generate_image_bit_exact(g_flow, name, sT, sI, rt):
                                  cfg_renorm_type=rt, cfg_interval=[0.4, 1.0], cfg_text_scale=sT,
                                  cfg_text=br(kv_t, rp_t, c_txt), cfg_img_scale=sI, cfg_img=br(kv_i, rp_i, c_img))
     assert torch.equal(torch.cat(lat, 0), g_flow[f"gen.{name}.latents"])
+
+
+def test_generate_text_greedy_bit_exact(g_flow):
+    """Bit-exact greedy token ids (BASELINE north_star) for the oracle vs the reference on CPU."""
+    from copy import deepcopy
+    cfg = fixtures.TINY_LM
+    sd = helpers.flow_state_dict(cfg)
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    with torch.no_grad():
+        c, kv, rp, _ = _oracle_contexts(sd, fc, cfg)(True)
+        gs = obf.prepare_start_tokens(kv, rp, helpers.NEW_TOKEN_IDS["bos_token_id"])
+        for k, v in gs.items():
+            assert torch.equal(v, g_flow["start." + k]) and v.dtype == g_flow["start." + k].dtype, k
+        trace = []
+        toks = obf.generate_text(sd, fc, deepcopy(c), max_length=12, logits_trace=trace, **gs)
+    assert torch.equal(toks, g_flow["text.tokens"])
+    assert torch.equal(torch.stack(trace, 0), g_flow["text.logits"])
