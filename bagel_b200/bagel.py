@@ -55,6 +55,15 @@ def get_flattened_position_ids_interpolate(img_h, img_w, patch_size, max_num_pat
     return (bh[:, None] * max_num_patches_per_side + bw[None, :]).reshape(-1)
 
 
+def patchify(image: torch.Tensor, patch_size: int) -> torch.Tensor:
+    """[C, H, W] -> [(H/p)*(W/p), p*p*C], each patch flattened (row-in-patch, col-in-patch, channel) — the
+    order convert_conv2d_to_linear's W.permute(0,2,3,1) expects (reference data/data_utils.py:43-50)."""
+    c, h, w = image.shape
+    p = patch_size
+    assert h % p == 0 and w % p == 0
+    return image.reshape(c, h // p, p, w // p, p).permute(1, 3, 2, 4, 0).reshape(-1, p * p * c)
+
+
 class _Affine:
     """weight/bias holder for vae2llm / llm2vae."""
 
@@ -189,7 +198,9 @@ class Bagel:
 
     def prepare_start_tokens(self, curr_kvlens, curr_rope, new_token_ids):
         cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
-        b_start = torch.cumsum(cl + 1, 0) - (cl + 1)
+        # NB: like the reference (:909-927) these indexes do NOT leave a slot for the query token; generate_text
+        # shifts sample i by i at the first step (:955-958).
+        b_start = torch.cumsum(cl, 0) - cl
         B = len(curr_kvlens)
         return {
             "packed_start_tokens": torch.tensor([new_token_ids["bos_token_id"]] * B, dtype=torch.long),
@@ -210,6 +221,68 @@ class Bagel:
             packed_query_position_ids=packed_text_position_ids, packed_query_indexes=packed_text_indexes,
             past_key_values=past_key_values, packed_key_value_indexes=packed_key_value_indexes,
             key_values_lens=key_values_lens, update_past_key_values=True, is_causal=True, mode="und")
+        return out.past_key_values
+
+    # ------------------------------------------------------------------------------------------
+    # image understanding context: SigLIP tokens (reference bagel.py:299-415)
+    # ------------------------------------------------------------------------------------------
+    def prepare_vit_images(self, curr_kvlens, curr_rope, images, transforms, new_token_ids):
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        rope = torch.tensor(list(curr_rope), dtype=torch.int64)
+        tokens, pos = [], []
+        for image in images:
+            t = transforms(image)
+            pos.append(self.get_flattened_position_ids(t.size(1), t.size(2), self.vit_patch_size,
+                                                       max_num_patches_per_side=self.vit_max_num_patch_per_side))
+            tokens.append(patchify(t, self.vit_patch_size))
+        ntok = torch.tensor([x.shape[0] for x in tokens], dtype=torch.int64)
+        ql = ntok + 2
+        q_start = torch.cumsum(ql, 0) - ql
+        b_start = torch.cumsum(cl + ql, 0) - (cl + ql)
+        B = len(images)
+        generation_input = {
+            "packed_text_ids": torch.tensor([new_token_ids["start_of_image"], new_token_ids["end_of_image"]] * B,
+                                            dtype=torch.long),
+            "packed_text_indexes": torch.stack([q_start, q_start + ntok + 1], dim=1).reshape(-1),
+            "vit_token_seqlens": ntok.to(torch.int),
+            "packed_vit_tokens": torch.cat(tokens, dim=0),
+            "packed_vit_position_ids": torch.cat(pos, dim=0),
+            "packed_vit_token_indexes": _ranges(q_start + 1, ntok),
+            "packed_position_ids": torch.repeat_interleave(rope, ql),
+            "packed_seqlens": ql.to(torch.int),
+            "packed_indexes": _ranges(b_start + cl, ql),
+            "packed_key_value_indexes": _ranges(b_start, cl),
+            "key_values_lens": cl.to(torch.int),
+        }
+        # an image block shares ONE rope position; the counter then advances by 1 (reference :340-343)
+        return generation_input, (cl + ql).tolist(), (rope + 1).tolist()
+
+    @torch.no_grad()
+    def forward_cache_update_vit(self, past_key_values: NaiveCache, packed_text_ids, packed_text_indexes,
+                                 packed_vit_tokens, packed_vit_token_indexes, packed_vit_position_ids,
+                                 vit_token_seqlens, packed_position_ids, packed_seqlens, packed_indexes,
+                                 packed_key_value_indexes, key_values_lens):
+        dev = self.device
+        lm = self.language_model.model
+        n = int(torch.as_tensor(packed_seqlens).sum())
+        seq = torch.zeros((n, self.hidden_size), dtype=BF16, device=dev)
+        emb = lm.embed_tokens(torch.as_tensor(packed_text_ids))
+        ops.copy_rows(emb, seq, dst_rows=torch.as_tensor(packed_text_indexes).to(dev, torch.int32))
+        vl = torch.as_tensor(vit_token_seqlens).to("cpu", torch.int64)
+        cu = torch.cat([torch.zeros(1, dtype=torch.int64), vl.cumsum(0)]).to(torch.int32)
+        feats = self.vit_model(packed_pixel_values=packed_vit_tokens,
+                               packed_flattened_position_ids=packed_vit_position_ids, cu_seqlens=cu,
+                               max_seqlen=int(vl.max()))
+        feats = self.connector(feats)
+        # + vit_pos_embed[pos], scattered to the image rows of the packed sequence (reference :390-395)
+        ops.latent_embed_add(feats, None, self.vit_pos_embed.pos_embed,
+                             torch.as_tensor(packed_vit_position_ids).to(dev, torch.int64).contiguous(), seq,
+                             torch.as_tensor(packed_vit_token_indexes).to(dev, torch.int32))
+        out = self.language_model.forward_inference(
+            packed_query_sequence=seq, query_lens=packed_seqlens, packed_query_position_ids=packed_position_ids,
+            packed_query_indexes=packed_indexes, past_key_values=past_key_values,
+            packed_key_value_indexes=packed_key_value_indexes, key_values_lens=key_values_lens,
+            update_past_key_values=True, is_causal=False, mode="und")
         return out.past_key_values
 
     # ------------------------------------------------------------------------------------------

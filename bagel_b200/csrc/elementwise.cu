@@ -72,6 +72,68 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm with affine (nn.LayerNorm in SiglipEncoderLayer / post_layernorm, modeling/bagel/siglip_navit.py:
+// 269-271, 283, 294, 346, 370): y = bf16( (x - mean) * rsqrt(var + eps) * w + b ), biased variance, fp32 math.
+// One warp per row, row held in registers (single HBM pass).
+// ---------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                 const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long ldy, int N, int H,
+                 float eps) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const int nvec = H >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s += bf16_lo(u[e]) + bf16_hi(u[e]);
+    }
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_lo(u[e]) - mean, c = bf16_hi(u[e]) - mean;
+        ss += a * a + c * c;
+      }
+    }
+  }
+  const float r = rsqrtf(warp_sum(ss) / (float)H + eps);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  const uint4* br = reinterpret_cast<const uint4*>(b);
+  uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const uint4 wv = wr[idx], bv = br[idx];
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = pack_bf16x2((bf16_lo(u[e]) - mean) * r * bf16_lo(ww[e]) + bf16_lo(bb[e]),
+                           (bf16_hi(u[e]) - mean) * r * bf16_hi(ww[e]) + bf16_hi(bb[e]));
+      yr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // RoPE tables (Qwen2RotaryEmbedding.forward, modeling_qwen2.py:130-150): angle = pos * inv_freq in fp32,
 // cos/sin optionally rounded to bf16 (the reference casts them to the hidden-stream dtype). Halves are
 // duplicated in the reference; we store D/2 columns.
@@ -206,7 +268,7 @@ latent_embed_add_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, c
   const uint4* pt = reinterpret_cast<const uint4*>(pos_table + pos_ids[i] * ldt);
   uint4* d = reinterpret_cast<uint4*>(seq + (long long)(dst_rows ? dst_rows[i] : i) * lds);
   for (int v = lane; v < (H >> 3); v += 32) {
-    const uint4 a = pr[v], b = te[v], c = pt[v];
+    const uint4 a = pr[v], b = (t_emb != nullptr) ? te[v] : make_uint4(0u, 0u, 0u, 0u), c = pt[v];
     const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w}, uc[4] = {c.x, c.y, c.z, c.w};
     uint32_t o[4];
 #pragma unroll
@@ -365,6 +427,30 @@ extern "C" int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, 
   else if (vpl <= 32) RMS_CASE(32);
   else return set_error(BAGEL_ERR_SHAPE, "bagel_rmsnorm_bf16: H=%d too large (max 8192)", H);
 #undef RMS_CASE
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y,
+                                    long long ldy, int N, int H, float eps, void* stream) {
+  if (N <= 0) return 0;
+  if ((H % 8) || (ldx % 8) || (ldy % 8)) return set_error(BAGEL_ERR_ALIGN, "bagel_layernorm_bf16: H, ldx, ldy must be multiples of 8");
+  const int vpl = (H / 8 + 31) / 32;
+  dim3 grid((N + 3) / 4), block(128);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto W = static_cast<const __nv_bfloat16*>(w);
+  auto B = static_cast<const __nv_bfloat16*>(b);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+#define LN_CASE(V) layernorm_kernel<V><<<grid, block, 0, s>>>(X, ldx, W, B, Y, ldy, N, H, eps)
+  if (vpl <= 1) LN_CASE(1);
+  else if (vpl <= 2) LN_CASE(2);
+  else if (vpl <= 5) LN_CASE(5);
+  else if (vpl <= 8) LN_CASE(8);
+  else if (vpl <= 16) LN_CASE(16);
+  else return set_error(BAGEL_ERR_SHAPE, "bagel_layernorm_bf16: H=%d too large (max 4096)", H);
+#undef LN_CASE
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;

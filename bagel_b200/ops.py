@@ -135,6 +135,17 @@ def rmsnorm(x: torch.Tensor, w0: torch.Tensor, w1: Optional[torch.Tensor] = None
     return out
 
 
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, out: Optional[torch.Tensor] = None):
+    _req(x, torch.bfloat16, "x"); _req(w, torch.bfloat16, "w"); _req(b, torch.bfloat16, "b")
+    N, H = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _cabi.lib().bagel_layernorm_bf16(_ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(out), out.stride(0), N, H,
+                                          float(eps), _stream())
+    _cabi.check(rc, "bagel_layernorm_bf16")
+    return out
+
+
 def rope_table(pos: torch.Tensor, inv_freq: torch.Tensor, round_bf16: bool = True):
     _req(pos, torch.int64, "pos"); _req(inv_freq, torch.float32, "inv_freq")
     N, half = pos.numel(), inv_freq.numel()
@@ -168,6 +179,7 @@ def copy_rows(src, dst, src_rows=None, dst_rows=None, M: Optional[int] = None):
 
 
 def latent_embed_add(proj, t_emb, pos_table, pos_ids, seq, dst_rows):
+    """seq[dst_rows[i]] = bf16(bf16(proj[i] + t_emb) + pos_table[pos_ids[i]]); t_emb / dst_rows may be None."""
     M, H = proj.shape
     _req(pos_ids, torch.int64, "pos_ids")
     rc = _cabi.lib().bagel_latent_embed_add(_ptr(proj), proj.stride(0), _ptr(t_emb), _ptr(pos_table), pos_table.stride(0),

@@ -77,6 +77,11 @@ int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out
 int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, const void* w1, const uint8_t* expert, void* y,
                        long long ldy, int N, int H, float eps, void* stream);
 
+/* y = bf16((x - mean) * rsqrt(var + eps) * w + b): nn.LayerNorm of the SigLIP tower
+ * (modeling/bagel/siglip_navit.py:269-271, 283, 294, 346, 370). x, y bf16 [N, H]; w, b bf16 [H]. */
+int bagel_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, int N,
+                         int H, float eps, void* stream);
+
 /* cos/sin[N, half] = cos/sin(float(pos[r]) * inv_freq[c]), optionally rounded to bf16 values
  * (Qwen2RotaryEmbedding.forward, modeling/qwen2/modeling_qwen2.py:130-150; halves are duplicated there). */
 int bagel_rope_table(const long long* pos, const float* inv_freq, float* cos_t, float* sin_t, int N, int half,
@@ -98,7 +103,9 @@ int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void* q_w0, cons
 int bagel_copy_rows_bf16(const void* src, long long lds, const int* src_rows, void* dst, long long ldd,
                          const int* dst_rows, int M, int H, void* stream);
 
-/* seq[dst_rows[i]] = bf16(bf16(proj[i] + t_emb) + pos_table[pos_ids[i]])  (modeling/bagel/bagel.py:801-806). */
+/* seq[dst_rows[i]] = bf16(bf16(proj[i] + t_emb) + pos_table[pos_ids[i]])  (modeling/bagel/bagel.py:801-806);
+ * t_emb NULL: seq = bf16(proj + pos_table[pos_ids]) (SigLIP patch embed + position embedding, siglip_navit.py:190-193;
+ * connector output + vit_pos_embed, bagel.py:390-392). */
 int bagel_latent_embed_add(const void* proj, long long ldp, const void* t_emb, const void* pos_table, long long ldt,
                            const long long* pos_ids, void* seq, long long lds, const int* dst_rows, int M, int H,
                            void* stream);

@@ -91,3 +91,44 @@ def config1_inputs(cfg: LMConfig = TINY_LM, seq: int = 512, seed: int = 0, dtype
         "text_indexes": torch.tensor([0, seq - 1], dtype=torch.long),
         "vae_indexes": torch.arange(1, seq - 1, dtype=torch.long),
     }
+
+
+def vit_state_dict(hidden: int, inter: int, layers: int, heads: int, llm_hidden: int, patch: int = 14,
+                   max_side: int = 8, seed: int = 3, dtype=torch.bfloat16, w_std: float = 0.05) -> Dict[str, torch.Tensor]:
+    """SigLIP NaViT tower (linear patch embedding, learned position table) + connector, reference key names."""
+    g = torch.Generator().manual_seed(seed)
+    pd = 3 * patch * patch
+    p = "vit_model.vision_model."
+    sd = {
+        p + "embeddings.patch_embedding.weight": _normal(g, (hidden, pd), w_std),
+        p + "embeddings.patch_embedding.bias": _normal(g, (hidden,), 0.1),
+        p + "embeddings.position_embedding.weight": _normal(g, (max_side * max_side, hidden), 0.5),
+        p + "post_layernorm.weight": 1.0 + _normal(g, (hidden,), 0.1),
+        p + "post_layernorm.bias": _normal(g, (hidden,), 0.1),
+    }
+    for li in range(layers):
+        q = p + f"encoder.layers.{li}."
+        for n in ("q", "k", "v", "out"):
+            sd[q + f"self_attn.{n}_proj.weight"] = _normal(g, (hidden, hidden), w_std * 2)
+            sd[q + f"self_attn.{n}_proj.bias"] = _normal(g, (hidden,), 0.1)
+        for n in ("layer_norm1", "layer_norm2"):
+            sd[q + n + ".weight"] = 1.0 + _normal(g, (hidden,), 0.1)
+            sd[q + n + ".bias"] = _normal(g, (hidden,), 0.1)
+        sd[q + "mlp.fc1.weight"] = _normal(g, (inter, hidden), w_std * 2)
+        sd[q + "mlp.fc1.bias"] = _normal(g, (inter,), 0.1)
+        sd[q + "mlp.fc2.weight"] = _normal(g, (hidden, inter), w_std * 2)
+        sd[q + "mlp.fc2.bias"] = _normal(g, (hidden,), 0.1)
+    sd["connector.fc1.weight"] = _normal(g, (llm_hidden, hidden), w_std * 2)
+    sd["connector.fc1.bias"] = _normal(g, (llm_hidden,), 0.1)
+    sd["connector.fc2.weight"] = _normal(g, (llm_hidden, llm_hidden), w_std)
+    sd["connector.fc2.bias"] = _normal(g, (llm_hidden,), 0.1)
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+TINY_VIT = dict(hidden=144, inter=296, layers=2, heads=2)      # head_dim 72 like SigLIP-so400m (1152/16)
+
+
+def vit_images(seed: int = 4):
+    """Two 'already transformed' images [3,H,W] in [-1,1] with H,W multiples of the 14-px patch."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(3, 42, 56, generator=g) * 2 - 1, torch.rand(3, 28, 28, generator=g) * 2 - 1]

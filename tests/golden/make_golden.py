@@ -223,6 +223,75 @@ def golden_flow(ns):
     save_file(out, os.path.join(OUT, "flow_tiny.safetensors"))
 
 
+def golden_vit(ns):
+    """SigLIP NaViT tower (head_dim 72) + connector + ViT context prefill, then a text prefill on top."""
+    from oracle import siglip as osl
+    cfg = fixtures.TINY_LM
+    dtype = torch.bfloat16
+    tv = fixtures.TINY_VIT
+    sd = flow_state_dict(cfg, dtype)
+    sd.update(fixtures.vit_state_dict(tv["hidden"], tv["inter"], tv["layers"], tv["heads"], cfg.hidden_size, dtype=dtype))
+    lm_sd = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+    lm, rcfg = ref_lm(ns, cfg, lm_sd, dtype)
+    sn = ns.siglip_navit
+    vcfg = sn.SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                                 num_attention_heads=tv["heads"], num_channels=3, image_size=112, patch_size=14, rope=False)
+    vit = sn.SiglipVisionModel(vcfg)
+    vit.vision_model.embeddings.convert_conv2d_to_linear(vcfg)
+    bcfg = ns.bagel.BagelConfig(visual_gen=True, visual_und=True, llm_config=rcfg, vit_config=vcfg,
+                                vae_config=SimpleNamespace(downsample=8, z_channels=16), latent_patch_size=2,
+                                max_latent_size=8, vit_max_num_patch_per_side=8)
+    model = ns.bagel.Bagel(lm, vit, bcfg).eval()
+    ref_shims.cast_parameters(model, dtype)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("pos_embed" in k for k in missing.missing_keys), missing
+    sd_full = dict(sd)
+    sd_full["latent_pos_embed.pos_embed"] = model.latent_pos_embed.pos_embed.data.clone()
+    sd_full["vit_pos_embed.pos_embed"] = model.vit_pos_embed.pos_embed.data.clone()
+    assert torch.equal(obf.sincos_2d_table(cfg.hidden_size, 8).to(dtype), sd_full["vit_pos_embed.pos_embed"])
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"])
+    images = fixtures.vit_images()
+    out = {}
+    gi, kv, rp = model.prepare_vit_images([0, 0], [0, 0], images, lambda im: im, NEW_TOKEN_IDS)
+    ogi, okv, orp = osl.prepare_vit_images(vc, 8, [0, 0], [0, 0], images, NEW_TOKEN_IDS["start_of_image"],
+                                           NEW_TOKEN_IDS["end_of_image"])
+    assert kv == okv and rp == orp
+    for k in gi:
+        assert torch.equal(gi[k], ogi[k]) and gi[k].dtype == ogi[k].dtype, k
+        out["vit_in." + k] = gi[k].clone()
+    out["vit_in.kv_lens"] = torch.tensor(kv)
+    out["vit_in.ropes"] = torch.tensor(rp)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        cu = torch.nn.functional.pad(torch.cumsum(gi["vit_token_seqlens"], 0), (1, 0)).to(torch.int32)
+        feats = model.vit_model(packed_pixel_values=gi["packed_vit_tokens"],
+                                packed_flattened_position_ids=gi["packed_vit_position_ids"], cu_seqlens=cu,
+                                max_seqlen=int(gi["vit_token_seqlens"].max()))
+        rc = model.forward_cache_update_vit(ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers), **gi)
+        tok = IntTokenizer()
+        gt, kv2, rp2 = model.prepare_prompts(kv, rp, ["5 17 900", "8 8 100 4"], tok, NEW_TOKEN_IDS)
+        rc = model.forward_cache_update_text(rc, **gt)
+    with torch.no_grad():
+        ofeats = osl.vit_forward(sd_full, vc, ogi["packed_vit_tokens"], ogi["packed_vit_position_ids"],
+                                 ogi["vit_token_seqlens"])
+        oc = osl.forward_cache_update_vit(sd_full, cfg, vc, om.KVCache(cfg.num_hidden_layers), **ogi)
+        ogt, _, _ = obf.prepare_prompts(kv, rp, [[5, 17, 900], [8, 8, 100, 4]], 1000, 1001)
+        oc = obf.forward_cache_update_text(sd_full, fc_of(cfg), oc, **ogt)
+    assert torch.equal(feats, ofeats), "oracle ViT != reference"
+    for li in range(cfg.num_hidden_layers):
+        assert torch.equal(rc.key_cache[li], oc.key_cache[li]) and torch.equal(rc.value_cache[li], oc.value_cache[li])
+    out["vit.features"] = feats.contiguous()
+    out["vit.k_cache_last"] = rc.key_cache[cfg.num_hidden_layers - 1].contiguous()
+    out["vit.v_cache_last"] = rc.value_cache[cfg.num_hidden_layers - 1].contiguous()
+    print("ViT tower + ViT/text prefill: oracle == reference (bit-exact); feature |x| mean",
+          float(feats.float().abs().mean()))
+    save_file(out, os.path.join(OUT, "vit_tiny.safetensors"))
+
+
+def fc_of(cfg):
+    return obf.FlowConfig(lm=cfg, max_latent_size=8)
+
+
 def main():
     if not ref_shims.reference_available():
         raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
@@ -230,6 +299,7 @@ def main():
     ns = ref_shims.load_reference()
     golden_lm_config1(ns)
     golden_flow(ns)
+    golden_vit(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

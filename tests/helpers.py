@@ -40,3 +40,33 @@ def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, 
     if load:
         model.load_state_dict(flow_state_dict(cfg, max_latent_size=max_latent_size))
     return model
+
+
+def vit_flow_state_dict(cfg=fixtures.TINY_LM, dtype=torch.bfloat16, max_latent_size=8):
+    tv = fixtures.TINY_VIT
+    sd = flow_state_dict(cfg, dtype, max_latent_size)
+    sd.update(fixtures.vit_state_dict(tv["hidden"], tv["inter"], tv["layers"], tv["heads"], cfg.hidden_size, dtype=dtype))
+    sd["vit_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 8).to(dtype)
+    return sd
+
+
+def build_product_bagel_with_vit(cfg=fixtures.TINY_LM, device="cuda", load=True):
+    from bagel_b200.bagel import Bagel
+    from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config, SiglipVisionConfig
+    from bagel_b200.qwen2_navit import Qwen2ForCausalLM
+    from bagel_b200.siglip_navit import SiglipVisionModel
+
+    tv = fixtures.TINY_VIT
+    llm = Qwen2Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                      num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                      num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta,
+                      rms_norm_eps=cfg.rms_norm_eps, qk_norm=True, layer_module="Qwen2MoTDecoderLayer")
+    vcfg = SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                              num_attention_heads=tv["heads"], num_channels=3, image_size=112, patch_size=14, rope=False)
+    bcfg = BagelConfig(visual_gen=True, visual_und=True, llm_config=llm, vit_config=vcfg,
+                       vae_config=AutoEncoderParams(), latent_patch_size=2, max_latent_size=8,
+                       vit_max_num_patch_per_side=8)
+    model = Bagel(Qwen2ForCausalLM(llm, device=device), SiglipVisionModel(vcfg, device=device), bcfg)
+    if load:
+        model.load_state_dict(vit_flow_state_dict(cfg))
+    return model

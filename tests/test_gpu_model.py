@@ -261,3 +261,37 @@ def test_generate_text_greedy(g_flow):
         logits = model.language_model.lm_head(out.packed_query_sequence).float().cpu()
         torch.testing.assert_close(logits, ref_logits[s], atol=0.06, rtol=0.02)
         kv, pos = kv + 1, pos + 1
+
+
+def test_vit_tower_and_image_understanding_prefill(golden_dir):
+    """SigLIP NaViT tower (head_dim 72 -> padded heads on the d=128 attention path), connector, ViT-context prefill
+    (non-causal image block) and a causal text prefill on top of it (BASELINE configs[2] shape, tiny model)."""
+    from bagel_b200.qwen2_navit import NaiveCache
+    from oracle import siglip as osl
+    g = load_file(os.path.join(golden_dir, "vit_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    model = helpers.build_product_bagel_with_vit(cfg, "cuda")
+    gi, kv, rp = model.prepare_vit_images([0, 0], [0, 0], fixtures.vit_images(), lambda im: im, helpers.NEW_TOKEN_IDS)
+    for k in gi:
+        assert torch.equal(gi[k], g["vit_in." + k]), k
+    vl = gi["vit_token_seqlens"]
+    cu = torch.cat([torch.zeros(1, dtype=torch.int64), vl.to(torch.int64).cumsum(0)]).to(torch.int32)
+    feats = model.vit_model(packed_pixel_values=gi["packed_vit_tokens"],
+                            packed_flattened_position_ids=gi["packed_vit_position_ids"], cu_seqlens=cu,
+                            max_seqlen=int(vl.max()))
+    # exact fp32 answer for the tower
+    tv = fixtures.TINY_VIT
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"])
+    sd32 = _f32(helpers.vit_flow_state_dict(cfg))
+    with torch.no_grad(), om.high_precision():
+        truth = osl.vit_forward(sd32, vc, gi["packed_vit_tokens"], gi["packed_vit_position_ids"], vl)
+    _check("vit features", feats, g["vit.features"], truth, max_ulps_of_scale=8.0)
+    cache = model.forward_cache_update_vit(NaiveCache(cfg.num_hidden_layers), **gi)
+    gt, kv2, rp2 = model.prepare_prompts(kv, rp, ["5 17 900", "8 8 100 4"], helpers.IntTokenizer(), helpers.NEW_TOKEN_IDS)
+    cache = model.forward_cache_update_text(cache, **gt)
+    torch.cuda.synchronize()
+    last = cfg.num_hidden_layers - 1
+    assert cache.key_cache[last].shape == g["vit.k_cache_last"].shape
+    _check("vit ctx k", cache.key_cache[last], g["vit.k_cache_last"], None)
+    _check("vit ctx v", cache.value_cache[last], g["vit.v_cache_last"], None)

@@ -126,3 +126,28 @@ def test_generate_text_greedy_bit_exact(g_flow):
         toks = obf.generate_text(sd, fc, deepcopy(c), max_length=12, logits_trace=trace, **gs)
     assert torch.equal(toks, g_flow["text.tokens"])
     assert torch.equal(torch.stack(trace, 0), g_flow["text.logits"])
+
+
+def test_vit_tower_and_context_bit_exact(golden_dir):
+    """SigLIP NaViT (head_dim 72) + connector + ViT-context prefill + text prefill on top: oracle == reference."""
+    import os
+    from oracle import siglip as osl
+    g = load_file(os.path.join(golden_dir, "vit_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    tv = fixtures.TINY_VIT
+    sd = helpers.vit_flow_state_dict(cfg)
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"])
+    gi, kv, rp = osl.prepare_vit_images(vc, 8, [0, 0], [0, 0], fixtures.vit_images(), 1002, 1003)
+    for k, v in gi.items():
+        assert torch.equal(v, g["vit_in." + k]) and v.dtype == g["vit_in." + k].dtype, k
+    assert kv == g["vit_in.kv_lens"].tolist() and rp == g["vit_in.ropes"].tolist()
+    with torch.no_grad():
+        feats = osl.vit_forward(sd, vc, gi["packed_vit_tokens"], gi["packed_vit_position_ids"], gi["vit_token_seqlens"])
+        assert torch.equal(feats, g["vit.features"])
+        c = osl.forward_cache_update_vit(sd, cfg, vc, om.KVCache(cfg.num_hidden_layers), **gi)
+        gt, _, _ = obf.prepare_prompts(kv, rp, [[5, 17, 900], [8, 8, 100, 4]], 1000, 1001)
+        c = obf.forward_cache_update_text(sd, obf.FlowConfig(lm=cfg, max_latent_size=8), c, **gt)
+    last = cfg.num_hidden_layers - 1
+    assert torch.equal(c.key_cache[last], g["vit.k_cache_last"])
+    assert torch.equal(c.value_cache[last], g["vit.v_cache_last"])

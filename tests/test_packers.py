@@ -67,7 +67,7 @@ def test_start_tokens(model):
     assert out["packed_start_tokens"].tolist() == [1000, 1000]
     assert out["packed_query_position_ids"].tolist() == [3, 1]
     assert out["key_values_lens"].tolist() == [3, 5] and out["key_values_lens"].dtype == torch.int32
-    assert out["packed_key_value_indexes"].tolist() == [0, 1, 2, 4, 5, 6, 7, 8]
+    assert out["packed_key_value_indexes"].tolist() == [0, 1, 2, 3, 4, 5, 6, 7]  # reference quirk: no query slot
 
 
 def test_position_ids_worked_example(model):
@@ -75,3 +75,12 @@ def test_position_ids_worked_example(model):
     from bagel_b200.bagel import get_flattened_position_ids_extrapolate as f
     assert f(32, 32, 16, 64).tolist() == [0, 1, 64, 65]
     assert f(32, 48, 16, 64).tolist() == [0, 1, 2, 64, 65, 66]
+
+
+def test_vit_packer_vs_reference_fixture(golden_dir):
+    m = helpers.build_product_bagel_with_vit(device="cpu", load=False)
+    g = load_file(os.path.join(golden_dir, "vit_tiny.safetensors"))
+    gi, kv, rp = m.prepare_vit_images([0, 0], [0, 0], fixtures.vit_images(), lambda im: im, helpers.NEW_TOKEN_IDS)
+    for k, v in gi.items():
+        assert torch.equal(v, g["vit_in." + k]) and v.dtype == g["vit_in." + k].dtype, k
+    assert kv == g["vit_in.kv_lens"].tolist() and rp == g["vit_in.ropes"].tolist()
