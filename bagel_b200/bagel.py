@@ -286,6 +286,76 @@ class Bagel:
         return out.past_key_values
 
     # ------------------------------------------------------------------------------------------
+    # image editing context: clean VAE latents at t=0 (reference bagel.py:417-550)
+    # ------------------------------------------------------------------------------------------
+    def prepare_vae_images(self, curr_kvlens, curr_rope, images, transforms, new_token_ids, timestep=0):
+        ds = self.latent_downsample
+        cl = torch.tensor(list(curr_kvlens), dtype=torch.int64)
+        rope = torch.tensor(list(curr_rope), dtype=torch.int64)
+        tensors = [transforms(im) for im in images]
+        shapes = [(t.shape[1] // ds, t.shape[2] // ds) for t in tensors]
+        ntok = torch.tensor([h * w for h, w in shapes], dtype=torch.int64)
+        ql = ntok + 2
+        q_start = torch.cumsum(ql, 0) - ql
+        b_start = torch.cumsum(cl + ql, 0) - (cl + ql)
+        B = len(images)
+        C = tensors[0].shape[0]
+        Hm, Wm = max(t.shape[1] for t in tensors), max(t.shape[2] for t in tensors)
+        padded = torch.zeros((B, C, Hm, Wm))
+        for i, t in enumerate(tensors):
+            padded[i, :, : t.shape[1], : t.shape[2]] = t
+        generation_input = {
+            "padded_images": padded,
+            "patchified_vae_latent_shapes": shapes,
+            "packed_vae_position_ids": torch.cat([self.get_flattened_position_ids(
+                t.size(1), t.size(2), ds, max_num_patches_per_side=self.max_latent_size) for t in tensors], dim=0),
+            "packed_timesteps": torch.tensor([timestep]),
+            "packed_vae_token_indexes": _ranges(q_start + 1, ntok),
+            "packed_text_ids": torch.tensor([new_token_ids["start_of_image"], new_token_ids["end_of_image"]] * B,
+                                            dtype=torch.long),
+            "packed_text_indexes": torch.stack([q_start, q_start + ntok + 1], dim=1).reshape(-1),
+            "packed_position_ids": torch.repeat_interleave(rope, ql),
+            "packed_seqlens": ql.to(torch.int),
+            "packed_indexes": _ranges(b_start + cl, ql),
+            "packed_key_value_indexes": _ranges(b_start, cl),
+            "key_values_lens": cl.to(torch.int),
+        }
+        return generation_input, (cl + ql).tolist(), (rope + 1).tolist()
+
+    @torch.no_grad()
+    def forward_cache_update_vae(self, vae_model, past_key_values: NaiveCache, padded_images,
+                                 patchified_vae_latent_shapes, packed_vae_position_ids, packed_timesteps,
+                                 packed_vae_token_indexes, packed_text_ids, packed_text_indexes, packed_position_ids,
+                                 packed_seqlens, packed_indexes, key_values_lens, packed_key_value_indexes):
+        dev = self.device
+        lm = self.language_model.model
+        n = int(torch.as_tensor(packed_seqlens).sum())
+        seq = torch.zeros((n, self.hidden_size), dtype=BF16, device=dev)
+        emb = lm.embed_tokens(torch.as_tensor(packed_text_ids))
+        ops.copy_rows(emb, seq, dst_rows=torch.as_tensor(packed_text_indexes).to(dev, torch.int32))
+        latents = vae_model.encode(padded_images)                      # [B, z, Hm/8, Wm/8]
+        p, zc = self.latent_patch_size, self.latent_channel
+        rows = []
+        for lat, (h, w) in zip(latents, patchified_vae_latent_shapes):  # 2x2 patchify, (p, q, c) order (:517-518)
+            lat = lat[:, : h * p, : w * p].reshape(zc, h, p, w, p)
+            rows.append(lat.permute(1, 3, 2, 4, 0).reshape(h * w, p * p * zc))
+        packed_latent = torch.cat(rows, dim=0).to(dev, BF16).contiguous()
+        proj = ops.gemm(packed_latent, self.vae2llm.weight, bias=self.vae2llm.bias)
+        t_emb = self.time_embedder(torch.as_tensor(packed_timesteps).to(dev, torch.float32).reshape(-1)[:1])
+        ops.latent_embed_add(proj, t_emb[0], self.latent_pos_embed.pos_embed,
+                             torch.as_tensor(packed_vae_position_ids).to(dev, torch.int64).contiguous(), seq,
+                             torch.as_tensor(packed_vae_token_indexes).to(dev, torch.int32))
+        extra = {}
+        if self.use_moe:
+            extra = dict(mode="gen", packed_vae_token_indexes=packed_vae_token_indexes,
+                         packed_text_indexes=packed_text_indexes)
+        out = self.language_model.forward_inference(
+            packed_query_sequence=seq, query_lens=packed_seqlens, packed_query_position_ids=packed_position_ids,
+            packed_query_indexes=packed_indexes, past_key_values=past_key_values, key_values_lens=key_values_lens,
+            packed_key_value_indexes=packed_key_value_indexes, update_past_key_values=True, is_causal=False, **extra)
+        return out.past_key_values
+
+    # ------------------------------------------------------------------------------------------
     # rectified-flow sampler
     # ------------------------------------------------------------------------------------------
     def _build_flow_plan(self, branches: List[Dict[str, Any]], packed_seqlens, packed_vae_token_indexes,

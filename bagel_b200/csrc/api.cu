@@ -83,6 +83,24 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
   return 0;
 }
 
+int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
+                           uint32_t box_w, uint32_t box_h, uint32_t stride) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(BAGEL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // with an element stride s the box spans box*s source elements and copies every s-th one
+  cuuint32_t box[4] = {box_c, box_w * stride, box_h * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(BAGEL_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d) dims=[%d,%d,%d,%d] box=[%u,%u,%u] stride=%u",
+                     (int)r, C, W, H, B, box_c, box_w, box_h, stride);
+  return 0;
+}
+
 }  // namespace bagel
 
 extern "C" const char* bagel_last_error(void) { return bagel::g_err; }

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -32,6 +33,7 @@ enum GemmEpilogue : int {
   EPI_SWIGLU = 2,  // C[:, j] = bf16(bf16(silu(bf16 g_j)) * bf16 u_j); W rows interleaved per 256 (128 g | 128 u)
   EPI_GELU = 3,    // C = bf16(gelu_tanh(bf16(acc + bias)))             (SigLIP MLP / connector)
   EPI_SILU = 4,    // C = bf16(silu(bf16(acc + bias)))                  (timestep MLP)
+  EPI_F32 = 5,     // C32 = acc (+ bias) as fp32                        (attention logits of the VAE mid block)
 };
 
 struct GemmParams {
@@ -44,6 +46,16 @@ struct GemmParams {
   const int* row_map;  // optional: output (and residual) row of A-row r is row_map[r]
   int num_m, num_n, num_tiles;
   int group_m;  // rasterisation: group_m M-tiles share one sweep over the N tiles (their A panels stay in L2)
+  // --- implicit-GEMM convolution (CONV kernels only): A is an NHWC activation tensor [B, Hi, Wi, Cin] read through a
+  // 4-D TMA map; an M tile is a th x tw patch of output pixels (th*tw = 128) of one image; K runs over
+  // (tap, 64-channel chunk); output / residual rows are NHWC pixel indices.
+  int Ho, Wo;            // output spatial size
+  int tw, th;            // tile width / height in output pixels
+  int tiles_w, tiles_h;  // tiles per image
+  int ksize, pad;        // 1 or 3; left/top zero padding in input pixels
+  int stride;            // 1 or 2 (the TMA map carries the element stride)
+  int cin_chunks;        // Cin / 64
+  float* C32;            // optional fp32 output (EPI_F32)
 };
 
 template <int BN>
@@ -73,7 +85,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -94,7 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k = (p.K + BK - 1) / BK;
+  const int num_k = CONV ? p.ksize * p.ksize * p.cin_chunks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -126,7 +138,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, kEvictNormal);
+          if constexpr (CONV) {
+            // m_blk -> (image, tile row, tile col); K block -> (tap, channel chunk). Out-of-image coordinates
+            // (the conv's zero padding, ragged tile edges) are zero-filled by TMA.
+            const int tiles_img = p.tiles_w * p.tiles_h;
+            const int img = m_blk / tiles_img, t_in = m_blk - img * tiles_img;
+            const int h0 = (t_in / p.tiles_w) * p.th, w0 = (t_in % p.tiles_w) * p.tw;
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cc * BK, w0 * p.stride + kw - p.pad,
+                        h0 * p.stride + kh - p.pad, img, kEvictNormal);
+          } else {
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, kEvictNormal);
+          }
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN, kEvictNormal);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -170,10 +194,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, p.num_m, p.num_n, p.group_m, m_blk, n_blk);
-      const int row = m_blk * BM + row_in_tile;
-      const bool row_ok = row < p.M;
-      long long out_row = row;
-      if (p.row_map != nullptr && row_ok) out_row = p.row_map[row];
+      int row;
+      bool row_ok;
+      long long out_row;
+      if constexpr (CONV) {
+        const int tiles_img = p.tiles_w * p.tiles_h;
+        const int img = m_blk / tiles_img, t_in = m_blk - img * tiles_img;
+        const int ho = (t_in / p.tiles_w) * p.th + row_in_tile / p.tw;
+        const int wo = (t_in % p.tiles_w) * p.tw + row_in_tile % p.tw;
+        row_ok = (ho < p.Ho) && (wo < p.Wo);
+        row = (img * p.Ho + ho) * p.Wo + wo;
+        out_row = row;
+      } else {
+        row = m_blk * BM + row_in_tile;
+        row_ok = row < p.M;
+        out_row = row;
+        if (p.row_map != nullptr && row_ok) out_row = p.row_map[row];
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -263,9 +300,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 x0 = silu_f(bf16_round(x0));
                 x1 = silu_f(bf16_round(x1));
               }
+              if constexpr (EPI == EPI_F32) {
+                float* d32 = p.C32 + out_row * p.ldc + n0 + 2 * j;
+                if (n0 + 2 * j < p.N) *reinterpret_cast<float2*>(d32) = make_float2(x0, x1);
+              }
               o[j] = pack_bf16x2(x0, x1);
             }
-            if (full) {
+            if constexpr (EPI == EPI_F32) {
+              // fp32 result already stored above
+            } else if (full) {
               uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
 #pragma unroll
               for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
@@ -295,16 +338,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, EPI, CONV>;
   static bool attr_done = false;  // per-instantiation; idempotent if raced
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  p.num_m = (p.M + BM - 1) / BM;
+  if (!CONV) p.num_m = (p.M + BM - 1) / BM;  // CONV: set by the caller (images x tiles per image)
   p.num_n = (p.N + BN - 1) / BN;
   p.num_tiles = p.num_m * p.num_n;
   // W is re-streamed from HBM once per M-group, so make the group as large as keeps its A panels (group_m x
@@ -313,7 +356,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     const long long panel = (long long)BM * p.K * 2;
     int g = 64;
     while (g > 4 && (long long)g * panel > (64ll << 20)) g >>= 1;
-    p.group_m = g;
+    static const int env_g = [] { const char* e = getenv("BAGEL_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
+    p.group_m = env_g > 0 ? env_g : g;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
@@ -330,6 +374,7 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case EPI_RESID: return launch_gemm<BN, EPI_RESID>(tmA, tmB, p, s);
     case EPI_GELU: return launch_gemm<BN, EPI_GELU>(tmA, tmB, p, s);
     case EPI_SILU: return launch_gemm<BN, EPI_SILU>(tmA, tmB, p, s);
+    case EPI_F32: return launch_gemm<BN, EPI_F32>(tmA, tmB, p, s);
     default: return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: unknown epilogue %d", epi);
   }
 }
@@ -358,6 +403,7 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   p.resid = static_cast<const __nv_bfloat16*>(resid);
   p.ldr = ldr;
   p.row_map = row_map;
+  p.C32 = static_cast<float*>(C);  // used by BAGEL_EPI_F32 only (C is then an fp32 [M, ldc] buffer)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   int bn;
@@ -375,4 +421,52 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   if (bn == 256) return dispatch_epi<256>(epilogue, tmA, tmB, p, s);
   if (bn == 128) return dispatch_epi<128>(epilogue, tmA, tmB, p, s);
   return dispatch_epi<64>(epilogue, tmA, tmB, p, s);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM 2-D convolution on NHWC bf16 activations (FLUX VAE: modeling/autoencoder.py:76-80, 102-108,
+// 114-119, 139, 170, 221, 248 — the reference runs these as cuDNN NCHW convolutions).
+//   out[b, ho, wo, :] = epilogue( sum_{kh,kw,c} x[b, ho*s + kh - pad, wo*s + kw - pad, c] * w[:, kh, kw, c] )
+// No im2col buffer: each (tap, 64-channel chunk) K-slice of the A tile is one 4-D TMA box whose signed
+// coordinates fall outside the image exactly where the convolution pads with zeros.
+// ---------------------------------------------------------------------------------------------
+extern "C" int bagel_conv2d_nhwc_bf16(const void* x, int B, int Hi, int Wi, int Cin, const void* w, int Cout, int ksize,
+                                      int stride, int pad, const void* bias, const void* resid, void* out, int Ho,
+                                      int Wo, void* stream) {
+  if (ksize != 1 && ksize != 3) return set_error(BAGEL_ERR_ARG, "bagel_conv2d_nhwc_bf16: ksize must be 1 or 3");
+  if (stride != 1 && stride != 2) return set_error(BAGEL_ERR_ARG, "bagel_conv2d_nhwc_bf16: stride must be 1 or 2");
+  if (Cin % 64) return set_error(BAGEL_ERR_SHAPE, "bagel_conv2d_nhwc_bf16: Cin must be a multiple of 64 (pad channels)");
+  if (Cout % 8) return set_error(BAGEL_ERR_SHAPE, "bagel_conv2d_nhwc_bf16: Cout must be a multiple of 8 (pad filters)");
+  if (B <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return set_error(BAGEL_ERR_SHAPE, "bagel_conv2d_nhwc_bf16: bad sizes");
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)resid) & 15)
+    return set_error(BAGEL_ERR_ALIGN, "bagel_conv2d_nhwc_bf16: pointers must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+
+  GemmParams p{};
+  p.Ho = Ho; p.Wo = Wo;
+  int tw = 128;
+  while (tw > Wo) tw >>= 1;  // largest power of two <= min(Wo, 128)
+  if (tw < 1) tw = 1;
+  p.tw = tw; p.th = 128 / tw;
+  p.tiles_w = (Wo + p.tw - 1) / p.tw;
+  p.tiles_h = (Ho + p.th - 1) / p.th;
+  p.ksize = ksize; p.pad = pad; p.stride = stride; p.cin_chunks = Cin / 64;
+  p.M = B * Ho * Wo; p.N = Cout; p.K = ksize * ksize * Cin;
+  p.num_m = B * p.tiles_w * p.tiles_h;
+  p.C = static_cast<__nv_bfloat16*>(out);
+  p.ldc = Cout;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.ldr = Cout;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_4d_nhwc_bf16(&tmA, x, B, Hi, Wi, Cin, 64, p.tw, p.th, stride)) return rc;
+  const int bn = (Cout % 256 == 0 || Cout >= 1024) ? 256 : (Cout > 64 ? 128 : 64);
+  if (int rc = make_tmap_2d_bf16(&tmB, w, (uint64_t)p.K, (uint64_t)Cout, (uint64_t)p.K, BK, bn)) return rc;
+  const bool res = resid != nullptr;
+  if (bn == 256) return res ? launch_gemm<256, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<256, EPI_BIAS, true>(tmA, tmB, p, s);
+  if (bn == 128) return res ? launch_gemm<128, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<128, EPI_BIAS, true>(tmA, tmB, p, s);
+  return res ? launch_gemm<64, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<64, EPI_BIAS, true>(tmA, tmB, p, s);
 }

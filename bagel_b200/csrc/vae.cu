@@ -1,0 +1,243 @@
+// HBM-bound kernels of the FLUX VAE (modeling/autoencoder.py): GroupNorm(32)+swish on NHWC activations,
+// nearest 2x upsampling, row softmax for the single-head d=512 mid attention, bf16 transpose.
+// The convolutions themselves are the implicit-GEMM tcgen05 kernel in gemm.cu (bagel_conv2d_nhwc_bf16).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace bagel {
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics, pass 1: partial (sum, sum of squares) per (image, slab, group).
+// x: [B, HW, C] bf16 (NHWC), G groups of C/G consecutive channels. Deterministic: no atomics, the slabs are
+// reduced in a fixed order by pass 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, long long HW, int C, int G,
+                  int slabs) {
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;  // 16-byte vectors per pixel
+  const long long pix0 = HW * slab / slabs, pix1 = HW * (slab + 1) / slabs;
+  const long long nvec = (pix1 - pix0) * vec_per_pix;
+  const uint4* base = reinterpret_cast<const uint4*>(x + ((long long)b * HW + pix0) * C);
+  __shared__ float4 part[256];  // per-thread (s0, q0, s1, q1); reduced in a fixed order -> deterministic
+  // a thread always visits the same vector slot of a pixel (blockDim % vec_per_pix == 0 is guaranteed by the host:
+  // vec_per_pix in {8,16,32,64}), so its channels -> groups mapping is fixed
+  const int slot = threadIdx.x % vec_per_pix;
+  const int c0 = slot * 8;
+  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;  // a vector of 8 channels spans 1 or 2 groups when cpg >= 4
+  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = base[i];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = bf16_lo(u[e]), c = bf16_hi(u[e]);
+      const int which = ((c0 + 2 * e) / cpg == g0) ? 0 : 1;
+      s[which] += a + c;
+      q[which] += a * a + c * c;
+    }
+  }
+  part[threadIdx.x] = make_float4(s[0], q[0], s[1], q[1]);
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float ss = 0.f, qq = 0.f;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      const int tc0 = (t % vec_per_pix) * 8;
+      const int tg0 = tc0 / cpg, tg1 = (tc0 + 7) / cpg;
+      const float4 v = part[t];
+      if (tg0 == g) { ss += v.x; qq += v.y; }
+      if (tg1 == g && tg1 != tg0) { ss += v.z; qq += v.w; }
+    }
+    partial[((long long)b * slabs + slab) * G + g] = make_float2(ss, qq);
+  }
+}
+
+// pass 2: reduce slabs -> (mean, rstd) per (image, group)
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int G, int slabs,
+                                   float count, float eps) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < slabs; ++i) {
+    const float2 p = partial[((long long)b * slabs + i) * G + g];
+    s += p.x;
+    q += p.y;
+  }
+  const double mean = s / count;
+  const double var = fmax(q / count - mean * mean, 0.0);
+  stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// pass 3: y = bf16( act( (x - mean) * rstd * w + b ) ), act = swish (x * sigmoid(x)) or identity
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ w,
+                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long HW, int C, int G,
+                int swish, long long total_vec) {
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / vec_per_pix;
+    const int c0 = (int)(i - pix * vec_per_pix) * 8;
+    const int b = (int)(pix / HW);
+    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    const float4 w0 = *reinterpret_cast<const float4*>(w + c0), w1 = *reinterpret_cast<const float4*>(w + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+    const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 st0 = stats[b * G + (c0 + 2 * e) / cpg];
+      const float2 st1 = stats[b * G + (c0 + 2 * e + 1) / cpg];
+      float a = (bf16_lo(u[e]) - st0.x) * st0.y * wf[2 * e] + bf[2 * e];
+      float c = (bf16_hi(u[e]) - st1.x) * st1.y * wf[2 * e + 1] + bf[2 * e + 1];
+      if (swish) {
+        a = a / (1.0f + __expf(-a));
+        c = c / (1.0f + __expf(-c));
+      }
+      o[e] = pack_bf16x2(a, c);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// nearest-neighbour 2x upsample, NHWC: y[b, 2h+i, 2w+j, :] = x[b, h, w, :]
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C,
+                  long long total_vec) {
+  const int vpp = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    long long pix = i / vpp;
+    const int wo = (int)(pix % (2 * W));
+    pix /= 2 * W;
+    const int ho = (int)(pix % (2 * H));
+    const long long b = pix / (2 * H);
+    const long long src = ((b * H + (ho >> 1)) * W + (wo >> 1)) * vpp + v;
+    reinterpret_cast<uint4*>(y)[i] = reinterpret_cast<const uint4*>(x)[src];
+  }
+}
+
+// P[r, :] = bf16(softmax(S[r, :] * scale)) — one block per row, fp32 logits (VAE mid attention, d = 512)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P, long long ldp, int L,
+                    float scale_log2) {
+  const long long r = blockIdx.x;
+  const float* s = S + r * lds;
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, s[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) sum += exp2f((s[i] - mx) * scale_log2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* p = P + r * ldp;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) p[i] = __float2bfloat16_rn(exp2f((s[i] - mx) * scale_log2) * inv);
+}
+
+// y[c, r] = x[r, c]  (bf16, 32x32 smem tiles)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                 int R, int Cc) {
+  __shared__ __nv_bfloat16 t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < Cc) ? x[(long long)r * ldx + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) y[(long long)c * ldy + r] = t[threadIdx.x][i];
+  }
+}
+
+}  // namespace bagel
+
+using namespace bagel;
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+extern "C" long long bagel_groupnorm_workspace_bytes(int B, int groups) {
+  const int slabs = 64;
+  return (long long)B * slabs * groups * sizeof(float2) + (long long)B * groups * sizeof(float2);
+}
+
+extern "C" int bagel_groupnorm_nhwc_bf16(const void* x, const void* w, const void* b, void* y, void* workspace, int B,
+                                         long long HW, int C, int groups, float eps, int swish, void* stream) {
+  if (B <= 0 || HW <= 0) return 0;
+  if (groups != 32) return set_error(BAGEL_ERR_ARG, "bagel_groupnorm_nhwc_bf16: groups must be 32");
+  const int vpp = C / 8;
+  if (C % 128 || (256 % vpp) != 0) return set_error(BAGEL_ERR_SHAPE, "bagel_groupnorm_nhwc_bf16: C must be 128, 256 or 512");
+  if (workspace == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_groupnorm_nhwc_bf16: workspace required");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int slabs = 64;
+  if (HW < slabs) slabs = (int)HW;
+  float2* partial = static_cast<float2*>(workspace);
+  float2* stats = partial + (long long)B * 64 * groups;
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  gn_partial_kernel<<<dim3(slabs, B), 256, 0, s>>>(X, partial, HW, C, groups, slabs);
+  COUNT_LAUNCH();
+  gn_finalize_kernel<<<B, 32, 0, s>>>(partial, stats, groups, slabs, (float)((double)HW * (C / groups)), eps);
+  COUNT_LAUNCH();
+  const long long total_vec = (long long)B * HW * vpp;
+  long long blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gn_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>(X, stats, static_cast<const float*>(w), static_cast<const float*>(b),
+                                                     static_cast<__nv_bfloat16*>(y), HW, C, groups, swish, total_vec);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (C % 8) return set_error(BAGEL_ERR_SHAPE, "bagel_upsample2x_nhwc_bf16: C %% 8");
+  const long long total_vec = (long long)B * 4 * H * W * (C / 8);
+  if (total_vec <= 0) return 0;
+  long long blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), H, W, C, total_vec);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_softmax_rows_f32(const float* S, long long lds, void* P, long long ldp, int rows, int L,
+                                      float scale, void* stream) {
+  if (rows <= 0 || L <= 0) return 0;
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, static_cast<__nv_bfloat16*>(P), ldp, L,
+                                                                          scale * 1.4426950408889634f);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_transpose_bf16(const void* x, long long ldx, void* y, long long ldy, int R, int Cc, void* stream) {
+  if (R <= 0 || Cc <= 0) return 0;
+  transpose_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, R, Cc);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

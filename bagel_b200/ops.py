@@ -9,7 +9,7 @@ import torch
 
 from . import _cabi
 
-EPI_BIAS, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_SILU = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_SILU, EPI_F32 = 0, 1, 2, 3, 4, 5
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -67,10 +67,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     N = w.shape[0]
     assert w.shape[1] == K
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    out_dtype = torch.float32 if epilogue == EPI_F32 else torch.bfloat16
     if out is None:
         assert row_map is None, "row_map scatter needs an explicit `out`"
-        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=a.device)
-    _req(out, torch.bfloat16, "out")
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    _req(out, out_dtype, "out")
     assert out.shape[1] == n_out
     if bias is not None:
         _req(bias, torch.bfloat16, "bias")
@@ -207,3 +208,81 @@ def cast_f32_to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
     rc = _cabi.lib().bagel_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream())
     _cabi.check(rc, "bagel_cast_f32_to_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# VAE ops (NHWC bf16)
+# ---------------------------------------------------------------------------------------------------------
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1, pad: int = 0,
+                out_hw=None, resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,H,W,Cin], w [Cout,k,k,Cin] bf16 -> [B,Ho,Wo,Cout] = bf16(resid + bf16(conv(x) + bias))."""
+    _req(x, torch.bfloat16, "x"); _req(w, torch.bfloat16, "w")
+    assert x.is_contiguous() and w.is_contiguous()
+    B, Hi, Wi, Cin = x.shape
+    Cout, k, k2, Cin2 = w.shape
+    assert k == k2 and Cin2 == Cin
+    if out_hw is None:
+        Ho = (Hi + 2 * pad - k) // stride + 1
+        Wo = (Wi + 2 * pad - k) // stride + 1
+    else:
+        Ho, Wo = out_hw
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    if resid is not None:
+        _req(resid, torch.bfloat16, "resid")
+        assert resid.shape == out.shape and resid.is_contiguous()
+    rc = _cabi.lib().bagel_conv2d_nhwc_bf16(_ptr(x), B, Hi, Wi, Cin, _ptr(w), Cout, k, stride, pad, _ptr(bias), _ptr(resid),
+                                            _ptr(out), Ho, Wo, _stream())
+    _cabi.check(rc, "bagel_conv2d_nhwc_bf16")
+    return out
+
+
+_gn_ws = {}
+
+
+def groupnorm_nhwc(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6, swish: bool = True,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    key = (x.device, B)
+    ws = _gn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(_cabi.lib().bagel_groupnorm_workspace_bytes(B, 32)), dtype=torch.uint8, device=x.device)
+        _gn_ws[key] = ws
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _cabi.lib().bagel_groupnorm_nhwc_bf16(_ptr(x), _ptr(w), _ptr(b), _ptr(out), _ptr(ws), B, HW, C, 32, float(eps),
+                                               int(swish), _stream())
+    _cabi.check(rc, "bagel_groupnorm_nhwc_bf16")
+    return out
+
+
+def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.bfloat16, device=x.device)
+    rc = _cabi.lib().bagel_upsample2x_nhwc_bf16(_ptr(x), _ptr(y), B, H, W, C, _stream())
+    _cabi.check(rc, "bagel_upsample2x_nhwc_bf16")
+    return y
+
+
+def softmax_rows(S: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(S, torch.float32, "S")
+    rows, L = S.shape
+    if out is None:
+        out = torch.empty((rows, L), dtype=torch.bfloat16, device=S.device)
+    rc = _cabi.lib().bagel_softmax_rows_f32(_ptr(S), S.stride(0), _ptr(out), out.stride(0), rows, L, float(scale), _stream())
+    _cabi.check(rc, "bagel_softmax_rows_f32")
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    R, Cc = x.shape
+    y = torch.empty((Cc, R), dtype=torch.bfloat16, device=x.device)
+    rc = _cabi.lib().bagel_transpose_bf16(_ptr(x), x.stride(0), _ptr(y), y.stride(0), R, Cc, _stream())
+    _cabi.check(rc, "bagel_transpose_bf16")
+    return y

@@ -42,6 +42,7 @@ long long bagel_launch_count(void);
 #define BAGEL_EPI_SWIGLU 2 /* C[:,j] = bf16(bf16(silu(bf16 g_j)) * bf16 u_j)         Qwen2MLP gate/up/act    */
 #define BAGEL_EPI_GELU 3   /* C = bf16(gelu_tanh(bf16(acc + bias)))                  SiglipMLP / connector   */
 #define BAGEL_EPI_SILU 4   /* C = bf16(silu(bf16(acc + bias)))                       TimestepEmbedder.mlp[0:2] */
+#define BAGEL_EPI_F32 5    /* C (fp32 [M, ldc]) = acc + bias                         attention logits, VAE mid block */
 
 /* C[M,N] = epilogue(A[M,K] @ W[N,K]^T), bf16 in / fp32 accumulate (tcgen05, TMEM) / bf16 out.
  * Replaces nn.Linear at modeling/bagel/qwen2_navit.py:515-517,529-536 (q/k/v_proj{,_moe_gen}),
@@ -120,6 +121,36 @@ int bagel_cfg_euler_step(const void* v, const void* v_text, const void* v_img, l
 
 /* y[i] = bf16(x[i]) — the autocast cast in front of vae2llm (modeling/bagel/bagel.py:803). */
 int bagel_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
+/* 2-D convolution on NHWC bf16 activations as an im2col-free implicit GEMM on tcgen05 (FLUX VAE convs:
+ * modeling/autoencoder.py:76-80 ResnetBlock, :102-108 Downsample (stride 2, pad right/bottom), :114-119 Upsample conv,
+ * :43-48 AttnBlock 1x1, :139,170,221,248 conv_in/conv_out — cuDNN NCHW convolutions in the reference).
+ *   x [B, Hi, Wi, Cin], w [Cout, ksize, ksize, Cin] (reference layout [Cout, Cin, kh, kw] permuted once at load),
+ *   out [B, Ho, Wo, Cout] = bf16(resid + bf16(conv + bias)) (resid / bias may be NULL).
+ *   ksize in {1, 3}; stride in {1, 2}; `pad` = zero padding on the left/top (right/bottom padding is implied by
+ *   Ho, Wo: anything outside the input reads as zero). Cin %% 64 == 0, Cout %% 8 == 0 (pad channels / filters). */
+int bagel_conv2d_nhwc_bf16(const void* x, int B, int Hi, int Wi, int Cin, const void* w, int Cout, int ksize, int stride,
+                           int pad, const void* bias, const void* resid, void* out, int Ho, int Wo, void* stream);
+
+/* GroupNorm(32 groups, affine) over NHWC bf16 [B, HW, C] + optional swish, fp32 statistics, deterministic two-stage
+ * reduction (modeling/autoencoder.py:43, 75-89, 169, 190-191, 247, 269-270 with swish :34-35).
+ * x, y bf16; w, b FP32 [C] (the reference keeps the VAE's parameters in fp32 and autocast runs group_norm in fp32);
+ * workspace: bagel_groupnorm_workspace_bytes(B, 32) bytes of device memory. C in {128, 256, 512}. */
+long long bagel_groupnorm_workspace_bytes(int B, int groups);
+int bagel_groupnorm_nhwc_bf16(const void* x, const void* w, const void* b, void* y, void* workspace, int B,
+                              long long HW, int C, int groups, float eps, int swish, void* stream);
+
+/* y[b, 2h+i, 2w+j, :] = x[b, h, w, :] — nn.functional.interpolate(scale_factor=2, mode="nearest")
+ * (modeling/autoencoder.py:117), NHWC bf16. */
+int bagel_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+
+/* P[r, :] = bf16(softmax(S[r, :] * scale)), S fp32 — softmax of the single-head d=512 attention of the VAE mid
+ * block (modeling/autoencoder.py:50-62, F.scaled_dot_product_attention). */
+int bagel_softmax_rows_f32(const float* S, long long lds, void* P, long long ldp, int rows, int L, float scale,
+                           void* stream);
+
+/* y[c, r] = x[r, c], bf16 (V^T for the P*V GEMM of the VAE mid attention). */
+int bagel_transpose_bf16(const void* x, long long ldx, void* y, long long ldy, int R, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -132,3 +132,62 @@ def vit_images(seed: int = 4):
     """Two 'already transformed' images [3,H,W] in [-1,1] with H,W multiples of the 14-px patch."""
     g = torch.Generator().manual_seed(seed)
     return [torch.rand(3, 42, 56, generator=g) * 2 - 1, torch.rand(3, 28, 28, generator=g) * 2 - 1]
+
+
+def vae_state_dict(ch: int = 128, ch_mult=(1, 2), num_res_blocks: int = 1, z_channels: int = 16, seed: int = 7,
+                   dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Random FLUX-VAE weights with the reference's key names (modeling/autoencoder.py module tree)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = _normal(g, (co, ci, k, k), (1.0 / (ci * k * k)) ** 0.5)
+        sd[name + ".bias"] = _normal(g, (co,), 0.05)
+
+    def norm(name, c):
+        sd[name + ".weight"] = 1.0 + _normal(g, (c,), 0.1)
+        sd[name + ".bias"] = _normal(g, (c,), 0.1)
+
+    def res(name, ci, co):
+        norm(name + ".norm1", ci); conv(name + ".conv1", co, ci, 3)
+        norm(name + ".norm2", co); conv(name + ".conv2", co, co, 3)
+        if ci != co:
+            conv(name + ".nin_shortcut", co, ci, 1)
+
+    def attn(name, c):
+        norm(name + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv(f"{name}.{n}", c, c, 1)
+
+    n = len(ch_mult)
+    in_mult = (1,) + tuple(ch_mult)
+    conv("encoder.conv_in", ch, 3, 3)
+    bi = ch
+    for lvl in range(n):
+        bi, bo = ch * in_mult[lvl], ch * ch_mult[lvl]
+        for i in range(num_res_blocks):
+            res(f"encoder.down.{lvl}.block.{i}", bi, bo)
+            bi = bo
+        if lvl != n - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", bi, bi, 3)
+    res("encoder.mid.block_1", bi, bi); attn("encoder.mid.attn_1", bi); res("encoder.mid.block_2", bi, bi)
+    norm("encoder.norm_out", bi); conv("encoder.conv_out", 2 * z_channels, bi, 3)
+    bi = ch * ch_mult[-1]
+    conv("decoder.conv_in", bi, z_channels, 3)
+    res("decoder.mid.block_1", bi, bi); attn("decoder.mid.attn_1", bi); res("decoder.mid.block_2", bi, bi)
+    for lvl in reversed(range(n)):
+        bo = ch * ch_mult[lvl]
+        for i in range(num_res_blocks + 1):
+            res(f"decoder.up.{lvl}.block.{i}", bi, bo)
+            bi = bo
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", bi, bi, 3)
+    norm("decoder.norm_out", bi); conv("decoder.conv_out", 3, bi, 3)
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def vae_inputs(seed: int = 8):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1          # ragged-vs-tile shape: W=48 is not a power of two
+    noise = torch.randn(2, 16, 16, 24, generator=g)
+    return img, noise

@@ -288,6 +288,39 @@ def golden_vit(ns):
     save_file(out, os.path.join(OUT, "vit_tiny.safetensors"))
 
 
+def golden_vae(ns):
+    """FLUX VAE encode (with a fixed DiagonalGaussian noise) and decode, tiny 2-level config, 2 images 32x48."""
+    from oracle import vae as ov
+    ae_mod = ns.autoencoder
+    params = ae_mod.AutoEncoderParams(resolution=32, in_channels=3, downsample=2, ch=128, out_ch=3, ch_mult=[1, 2],
+                                      num_res_blocks=1, z_channels=16, scale_factor=0.3611, shift_factor=0.1159)
+    ae = ae_mod.AutoEncoder(params).eval()
+    sd = fixtures.vae_state_dict()
+    ae.load_state_dict(sd, strict=True)
+    vc = ov.VaeConfig(ch=128, ch_mult=[1, 2], num_res_blocks=1)
+    img, noise = fixtures.vae_inputs()
+    out = {}
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        moments = ae.encoder(img)
+        ae.reg.sample = False
+        z_mean = ae.encode(img)
+        mean, logvar = torch.chunk(moments, 2, dim=1)
+        z_noise = params.scale_factor * ((mean + torch.exp(0.5 * logvar) * noise) - params.shift_factor)
+        z_in = torch.randn(2, 16, 16, 24, generator=torch.Generator().manual_seed(9))
+        rec = ae.decode(z_in)
+    with torch.no_grad():
+        oz_mean = ov.encode(sd, vc, img)
+        oz_noise = ov.encode(sd, vc, img, noise)
+        orec = ov.decode(sd, vc, z_in)
+    assert torch.equal(z_mean, oz_mean) and torch.equal(z_noise, oz_noise), "oracle VAE encode != reference"
+    assert torch.equal(rec, orec), "oracle VAE decode != reference"
+    out["vae.z_mean"], out["vae.z_noise"] = z_mean.contiguous(), z_noise.contiguous()
+    out["vae.z_in"], out["vae.rec"] = z_in.contiguous(), rec.contiguous()
+    print("VAE encode/decode: oracle == reference (bit-exact); |rec| mean", float(rec.float().abs().mean()),
+          "|z| mean", float(z_mean.float().abs().mean()))
+    save_file(out, os.path.join(OUT, "vae_tiny.safetensors"))
+
+
 def fc_of(cfg):
     return obf.FlowConfig(lm=cfg, max_latent_size=8)
 
@@ -300,6 +333,7 @@ def main():
     golden_lm_config1(ns)
     golden_flow(ns)
     golden_vit(ns)
+    golden_vae(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

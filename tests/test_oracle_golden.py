@@ -151,3 +151,16 @@ def test_vit_tower_and_context_bit_exact(golden_dir):
     last = cfg.num_hidden_layers - 1
     assert torch.equal(c.key_cache[last], g["vit.k_cache_last"])
     assert torch.equal(c.value_cache[last], g["vit.v_cache_last"])
+
+
+def test_vae_bit_exact(golden_dir):
+    import os
+    from oracle import vae as ov
+    g = load_file(os.path.join(golden_dir, "vae_tiny.safetensors"))
+    sd = fixtures.vae_state_dict()
+    vc = ov.VaeConfig(ch=128, ch_mult=[1, 2], num_res_blocks=1)
+    img, noise = fixtures.vae_inputs()
+    with torch.no_grad():
+        assert torch.equal(ov.encode(sd, vc, img), g["vae.z_mean"])
+        assert torch.equal(ov.encode(sd, vc, img, noise), g["vae.z_noise"])
+        assert torch.equal(ov.decode(sd, vc, g["vae.z_in"]), g["vae.rec"])
