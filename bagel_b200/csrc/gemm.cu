@@ -350,14 +350,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   if (!CONV) p.num_m = (p.M + BM - 1) / BM;  // CONV: set by the caller (images x tiles per image)
   p.num_n = (p.N + BN - 1) / BN;
   p.num_tiles = p.num_m * p.num_n;
-  // W is re-streamed from HBM once per M-group, so make the group as large as keeps its A panels (group_m x
-  // 128 x K bf16) comfortably inside the 126 MB L2: ncu showed 9.4 GB of DRAM reads for 0.74 GB of operands at 16.
+  // Raster group: group_m M-tiles share one sweep over the N tiles. Measured on B200 at M=65568 (A/B in one process
+  // per value, profiles/r01_gemm_group_ab.txt): wide outputs (148 N-tiles, gate|up) are fastest at 16, narrow ones
+  // (14-18 N-tiles: qkv, o_proj, down_proj) at 32; 8 and 64 lose 5-15 % either way.
   {
-    const long long panel = (long long)BM * p.K * 2;
-    int g = 64;
-    while (g > 4 && (long long)g * panel > (64ll << 20)) g >>= 1;
     static const int env_g = [] { const char* e = getenv("BAGEL_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
-    p.group_m = env_g > 0 ? env_g : g;
+    p.group_m = env_g > 0 ? env_g : (p.num_n >= 64 ? 16 : 32);
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);

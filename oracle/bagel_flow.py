@@ -286,3 +286,64 @@ def generate_text(sd, fc: FlowConfig, past_key_values, packed_key_value_indexes,
         if end_token_id is not None and cur[0] == end_token_id:
             break
     return torch.stack(seq, dim=0)
+
+
+def prepare_vae_images(fc: FlowConfig, curr_kvlens, curr_rope, image_tensors, soi, eoi, timestep=0):
+    """bagel.py:417-488 with `transforms` already applied."""
+    shapes, vpos, v_idx, t_ids, t_idx, seqlens, pos, q_idx, kv_idx = [], [], [], [], [], [], [], [], []
+    qc = cur = 0
+    newlens, newrope = [], []
+    for img, kvlen, rope in zip(image_tensors, curr_kvlens, curr_rope):
+        kv_idx += list(range(cur, cur + kvlen)); cur += kvlen
+        t_ids.append(soi); t_idx.append(qc); q_idx.append(cur); cur += 1; qc += 1
+        vpos.append(flattened_position_ids(img.size(1), img.size(2), fc.latent_downsample, fc.max_latent_size))
+        h, w = img.shape[1] // fc.latent_downsample, img.shape[2] // fc.latent_downsample
+        shapes.append((h, w)); n = h * w
+        v_idx += list(range(qc, qc + n)); q_idx += list(range(cur, cur + n)); cur += n; qc += n
+        t_ids.append(eoi); t_idx.append(qc); q_idx.append(cur); cur += 1; qc += 1
+        pos += [rope] * (n + 2); seqlens.append(n + 2)
+        newlens.append(kvlen + n + 2); newrope.append(rope + 1)
+    sizes = [t.shape for t in image_tensors]
+    mx = [max(v) for v in zip(*sizes)]
+    padded = torch.zeros((len(image_tensors), *mx))
+    for i, t in enumerate(image_tensors):
+        padded[i, :, : t.shape[1], : t.shape[2]] = t
+    gi = {
+        "padded_images": padded, "patchified_vae_latent_shapes": shapes,
+        "packed_vae_position_ids": torch.cat(vpos, dim=0), "packed_timesteps": torch.tensor([timestep]),
+        "packed_vae_token_indexes": torch.tensor(v_idx, dtype=torch.long),
+        "packed_text_ids": torch.tensor(t_ids, dtype=torch.long),
+        "packed_text_indexes": torch.tensor(t_idx, dtype=torch.long),
+        "packed_position_ids": torch.tensor(pos, dtype=torch.long),
+        "packed_seqlens": torch.tensor(seqlens, dtype=torch.int),
+        "packed_indexes": torch.tensor(q_idx, dtype=torch.long),
+        "packed_key_value_indexes": torch.tensor(kv_idx, dtype=torch.long),
+        "key_values_lens": torch.tensor(curr_kvlens, dtype=torch.int),
+    }
+    return gi, newlens, newrope
+
+
+def forward_cache_update_vae(sd, fc: FlowConfig, vae_encode, cache, padded_images, patchified_vae_latent_shapes,
+                             packed_vae_position_ids, packed_timesteps, packed_vae_token_indexes, packed_text_ids,
+                             packed_text_indexes, packed_position_ids, packed_seqlens, packed_indexes, key_values_lens,
+                             packed_key_value_indexes):
+    """bagel.py:491-550; `vae_encode(images) -> latents [B, z, H/8, W/8]` stands for vae_model.encode."""
+    emb = F.embedding(packed_text_ids, sd["language_model.model.embed_tokens.weight"])
+    seq = emb.new_zeros((int(sum(packed_seqlens)), fc.lm.hidden_size))
+    seq[packed_text_indexes] = emb
+    lat = vae_encode(padded_images)
+    p = fc.latent_patch_size
+    rows = []
+    for z, (h, w) in zip(lat, patchified_vae_latent_shapes):
+        z = z[:, : h * p, : w * p].reshape(fc.latent_channel, h, p, w, p)
+        rows.append(torch.einsum("chpwq->hwpqc", z).reshape(-1, p * p * fc.latent_channel))
+    packed = torch.cat(rows, dim=0)
+    packed = linear(packed, sd["vae2llm.weight"], sd["vae2llm.bias"]) + time_embedder(sd, packed_timesteps) \
+        + sd["latent_pos_embed.pos_embed"][packed_vae_position_ids]
+    if packed.dtype != seq.dtype:
+        packed = packed.to(seq.dtype)
+    seq[packed_vae_token_indexes] = packed
+    _, cache = om.lm_forward_inference(lm_sub(sd), fc.lm, seq, packed_seqlens, packed_position_ids, packed_indexes,
+                                       cache, key_values_lens, packed_key_value_indexes, True, False, "gen",
+                                       packed_vae_token_indexes, packed_text_indexes)
+    return cache

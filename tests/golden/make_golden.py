@@ -316,6 +316,39 @@ def golden_vae(ns):
     assert torch.equal(rec, orec), "oracle VAE decode != reference"
     out["vae.z_mean"], out["vae.z_noise"] = z_mean.contiguous(), z_noise.contiguous()
     out["vae.z_in"], out["vae.rec"] = z_in.contiguous(), rec.contiguous()
+    # ---- VAE image as generation context (image-edit path): prepare_vae_images + forward_cache_update_vae ----
+    cfg = fixtures.TINY_LM
+    sdl = flow_state_dict(cfg, torch.bfloat16)
+    lm_sd = {k[len("language_model."):]: v for k, v in sdl.items() if k.startswith("language_model.")}
+    lm, rcfg = ref_lm(ns, cfg, lm_sd, torch.bfloat16)
+    bcfg = ns.bagel.BagelConfig(visual_gen=True, visual_und=False, llm_config=rcfg, vit_config=None,
+                                vae_config=SimpleNamespace(downsample=2, z_channels=16), latent_patch_size=2,
+                                max_latent_size=16)
+    model = ns.bagel.Bagel(lm, None, bcfg).eval()
+    ref_shims.cast_parameters(model, torch.bfloat16)
+    model.load_state_dict(sdl, strict=False)
+    sd_full = dict(sdl)
+    sd_full["latent_pos_embed.pos_embed"] = model.latent_pos_embed.pos_embed.data.clone()
+    fc = obf.FlowConfig(lm=cfg, vae_downsample=2, max_latent_size=16)
+    imgs = [img[0], img[1][:, :24, :32]]                       # ragged: 32x48 and 24x32
+    gi, kv, rp = model.prepare_vae_images([0, 0], [0, 0], imgs, lambda im: im, NEW_TOKEN_IDS)
+    ogi, okv, orp = obf.prepare_vae_images(fc, [0, 0], [0, 0], imgs, 1002, 1003)
+    assert kv == okv and rp == orp
+    for k in gi:
+        same = (gi[k] == ogi[k]) if isinstance(gi[k], list) else torch.equal(gi[k], ogi[k])
+        assert same, k
+        if torch.is_tensor(gi[k]):
+            out["vae_ctx." + k] = gi[k].clone()
+    out["vae_ctx.kv_lens"], out["vae_ctx.ropes"] = torch.tensor(kv), torch.tensor(rp)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        rc = model.forward_cache_update_vae(ae, ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers), **gi)
+    with torch.no_grad():
+        oc = obf.forward_cache_update_vae(sd_full, fc, lambda x: ov.encode(sd, vc, x), om.KVCache(cfg.num_hidden_layers), **ogi)
+    for li in range(cfg.num_hidden_layers):
+        assert torch.equal(rc.key_cache[li], oc.key_cache[li]) and torch.equal(rc.value_cache[li], oc.value_cache[li])
+    out["vae_ctx.k_cache_last"] = rc.key_cache[cfg.num_hidden_layers - 1].contiguous()
+    out["vae_ctx.v_cache_last"] = rc.value_cache[cfg.num_hidden_layers - 1].contiguous()
+    print("VAE-context prefill (DiagonalGaussian sample=False): oracle == reference (bit-exact)")
     print("VAE encode/decode: oracle == reference (bit-exact); |rec| mean", float(rec.float().abs().mean()),
           "|z| mean", float(z_mean.float().abs().mean()))
     save_file(out, os.path.join(OUT, "vae_tiny.safetensors"))

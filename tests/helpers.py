@@ -23,7 +23,16 @@ def flow_state_dict(cfg=fixtures.TINY_LM, dtype=torch.bfloat16, max_latent_size=
     return sd
 
 
-def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, load=True):
+def tiny_vae(device="cuda"):
+    from bagel_b200.autoencoder import AutoEncoder
+    from bagel_b200.config import AutoEncoderParams
+    ae = AutoEncoder(AutoEncoderParams(resolution=32, downsample=2, ch=128, ch_mult=[1, 2], num_res_blocks=1,
+                                       z_channels=16), device)
+    ae.load_state_dict(fixtures.vae_state_dict())
+    return ae
+
+
+def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, load=True, vae_downsample=8):
     """bagel_b200.Bagel for the tiny config (device='cpu' only exercises host logic: packers, config)."""
     from bagel_b200.bagel import Bagel
     from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config
@@ -34,7 +43,8 @@ def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, 
                       num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta,
                       rms_norm_eps=cfg.rms_norm_eps, qk_norm=True, layer_module="Qwen2MoTDecoderLayer")
     bcfg = BagelConfig(visual_gen=True, visual_und=False, llm_config=llm, vit_config=None,
-                       vae_config=AutoEncoderParams(), latent_patch_size=2, max_latent_size=max_latent_size)
+                       vae_config=AutoEncoderParams(downsample=vae_downsample), latent_patch_size=2,
+                       max_latent_size=max_latent_size)
     lm = Qwen2ForCausalLM(llm, device=device)
     model = Bagel(lm, None, bcfg)
     if load:

@@ -150,3 +150,28 @@ def test_vae_decode_shapes_at_model_resolution():
         with om.high_precision():
             truth = ov.decode(sd, vc, z)
     _check("decode 128x128", rec, ref, truth, ulps_of_scale=16.0)
+
+
+def test_vae_context_prefill_vs_reference(golden_dir):
+    """Image-edit context on the GPU: VAE encode -> 2x2 patchify -> vae2llm + t=0 embedding + 2-D sincos ->
+    MoT forward in gen mode with cache update (reference bagel.py:491-550)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__)))
+    import helpers
+    from bagel_b200.qwen2_navit import NaiveCache
+    g = load_file(os.path.join(golden_dir, "vae_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    model = helpers.build_product_bagel(cfg, "cuda", max_latent_size=16, vae_downsample=2, load=False)
+    model.load_state_dict(helpers.flow_state_dict(cfg, max_latent_size=16))
+    ae = helpers.tiny_vae("cuda")
+    ae.sample = False
+    img, _ = fixtures.vae_inputs()
+    gi, kv, rp = model.prepare_vae_images([0, 0], [0, 0], [img[0], img[1][:, :24, :32]], lambda im: im, helpers.NEW_TOKEN_IDS)
+    cache = model.forward_cache_update_vae(ae, NaiveCache(cfg.num_hidden_layers), **gi)
+    torch.cuda.synchronize()
+    last = cfg.num_hidden_layers - 1
+    for name, got, ref in (("k", cache.key_cache[last], g["vae_ctx.k_cache_last"]), ("v", cache.value_cache[last], g["vae_ctx.v_cache_last"])):
+        assert got.shape == ref.shape
+        scale = ref.float().abs().max().item()
+        err = (got.float().cpu() - ref.float()).abs().max().item()
+        assert err <= 8 * scale * 2 ** -8, f"{name}: {err:.4e} (scale {scale:.3f})"

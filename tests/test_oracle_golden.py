@@ -164,3 +164,30 @@ def test_vae_bit_exact(golden_dir):
         assert torch.equal(ov.encode(sd, vc, img), g["vae.z_mean"])
         assert torch.equal(ov.encode(sd, vc, img, noise), g["vae.z_noise"])
         assert torch.equal(ov.decode(sd, vc, g["vae.z_in"]), g["vae.rec"])
+
+
+def _vae_ctx_inputs():
+    img, _ = fixtures.vae_inputs()
+    return [img[0], img[1][:, :24, :32]]
+
+
+def test_vae_context_prefill_bit_exact(golden_dir):
+    """Image-edit context: prepare_vae_images + forward_cache_update_vae (VAE encode with sample=False)."""
+    import os
+    from oracle import vae as ov
+    g = load_file(os.path.join(golden_dir, "vae_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    sd = helpers.flow_state_dict(cfg, max_latent_size=16)
+    fc = obf.FlowConfig(lm=cfg, vae_downsample=2, max_latent_size=16)
+    vsd = fixtures.vae_state_dict()
+    vc = ov.VaeConfig(ch=128, ch_mult=[1, 2], num_res_blocks=1)
+    gi, kv, rp = obf.prepare_vae_images(fc, [0, 0], [0, 0], _vae_ctx_inputs(), 1002, 1003)
+    for k, v in gi.items():
+        if torch.is_tensor(v):
+            assert torch.equal(v, g["vae_ctx." + k]), k
+    assert kv == g["vae_ctx.kv_lens"].tolist() and rp == g["vae_ctx.ropes"].tolist()
+    with torch.no_grad():
+        c = obf.forward_cache_update_vae(sd, fc, lambda x: ov.encode(vsd, vc, x), om.KVCache(cfg.num_hidden_layers), **gi)
+    last = cfg.num_hidden_layers - 1
+    assert torch.equal(c.key_cache[last], g["vae_ctx.k_cache_last"])
+    assert torch.equal(c.value_cache[last], g["vae_ctx.v_cache_last"])

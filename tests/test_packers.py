@@ -84,3 +84,16 @@ def test_vit_packer_vs_reference_fixture(golden_dir):
     for k, v in gi.items():
         assert torch.equal(v, g["vit_in." + k]) and v.dtype == g["vit_in." + k].dtype, k
     assert kv == g["vit_in.kv_lens"].tolist() and rp == g["vit_in.ropes"].tolist()
+
+
+def test_vae_image_packer_vs_reference_fixture(golden_dir):
+    from bagel_b200.config import AutoEncoderParams
+    m = helpers.build_product_bagel(device="cpu", load=False, max_latent_size=16, vae_downsample=2)
+    g = load_file(os.path.join(golden_dir, "vae_tiny.safetensors"))
+    img, _ = fixtures.vae_inputs()
+    gi, kv, rp = m.prepare_vae_images([0, 0], [0, 0], [img[0], img[1][:, :24, :32]], lambda im: im, helpers.NEW_TOKEN_IDS)
+    for k, v in gi.items():
+        if torch.is_tensor(v):
+            assert torch.equal(v, g["vae_ctx." + k]) and v.dtype == g["vae_ctx." + k].dtype, k
+    assert gi["patchified_vae_latent_shapes"] == [(8, 12), (6, 8)]
+    assert kv == g["vae_ctx.kv_lens"].tolist() and rp == g["vae_ctx.ropes"].tolist()
