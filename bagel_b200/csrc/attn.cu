@@ -45,6 +45,23 @@ struct AttnCfg {
   static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256;
 };
 
+// packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of FMA / ADD
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -237,9 +254,15 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < kBlockN; ++i)
             if (kv0 + i > lim) s[i] = -INFINITY;
         }
-        float mx = s[0];
+        // 8 independent running maxima: a single serial fmax chain (128 dependent ops, 4-cycle latency each) is
+        // pure exposed latency with one softmax warp per scheduler
+        float mx8[8];
 #pragma unroll
-        for (int i = 1; i < kBlockN; ++i) mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+#pragma unroll
+        for (int i = 8; i < kBlockN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         const float m_new = fmaxf(m, mx);
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = ex2((m - m_use) * p.scale_log2);  // m = -inf -> 0
@@ -258,19 +281,23 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
         const float neg_ms = -m_use * p.scale_log2;
-        float rs = 0.f;
+        // x*scale - m*scale as packed f32x2 FMAs (Blackwell FFMA2: half the FMA-pipe issue slots), exp2 on the MUFU,
+        // four independent partial row sums (packed adds) instead of one serial chain
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
+        float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int c = 0; c < kBlockN / 64; ++c) {
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float p0 = ex2(fmaf(s[c * 64 + 2 * i], p.scale_log2, neg_ms));
-            const float p1 = ex2(fmaf(s[c * 64 + 2 * i + 1], p.scale_log2, neg_ms));
-            rs += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            const float2 x = ffma2(make_float2(s[c * 64 + 2 * i], s[c * 64 + 2 * i + 1]), sc2, nm2);
+            const float2 e = make_float2(ex2(x.x), ex2(x.y));
+            rs2[i & 1] = fadd2(rs2[i & 1], e);
+            pk[i] = pack_bf16x2(e.x, e.y);
           }
           tmem_st_x32(tS + c * 32, pk);
         }
+        const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
         m = m_new;
         tmem_st_wait();

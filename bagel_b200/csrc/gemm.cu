@@ -34,6 +34,20 @@ enum GemmEpilogue : int {
   EPI_GELU = 3,    // C = bf16(gelu_tanh(bf16(acc + bias)))             (SigLIP MLP / connector)
   EPI_SILU = 4,    // C = bf16(silu(bf16(acc + bias)))                  (timestep MLP)
   EPI_F32 = 5,     // C32 = acc (+ bias) as fp32                        (attention logits of the VAE mid block)
+  EPI_QKV = 6,     // fused q/k RMSNorm + RoPE + bf16 cast + K/V placement  (PackedAttentionMoT, head_dim 128)
+};
+
+// Extra arguments of the fused QKV epilogue (see bagel_gemm_qkv_norm_rope in include/bagel_b200.h).
+struct QkvEpi {
+  const __nv_bfloat16 *qw0, *kw0, *qw1, *kw1;  // per-head RMSNorm weights [128]: und expert / gen expert (may be null)
+  const uint8_t* expert;                       // [rows] 1 = gen expert
+  const float *cos_t, *sin_t;                  // [rows, 64]
+  __nv_bfloat16 *q_out, *k_out, *v_out;
+  long long ld_q, ld_kv;
+  const int* kv_rows;                          // destination row of each token in the merged K/V buffers
+  int Hq, Hk;
+  float eps;
+  int fp32_flow;
 };
 
 struct GemmParams {
@@ -56,6 +70,7 @@ struct GemmParams {
   int stride;            // 1 or 2 (the TMA map carries the element stride)
   int cin_chunks;        // Cin / 64
   float* C32;            // optional fp32 output (EPI_F32)
+  QkvEpi qkv;            // EPI_QKV only
 };
 
 template <int BN>
@@ -216,7 +231,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
 
-      if constexpr (EPI == EPI_SWIGLU) {
+      if constexpr (EPI == EPI_QKV) {
+        // Thread = one token row; a 256-wide tile = two heads of 128. Everything the reference does between the
+        // projection and flash-attn (qwen2_navit.py:518-519 / 542-574) happens here on the fp32 accumulators.
+        static_assert(BN == 256, "fused QKV epilogue: two 128-wide heads per tile");
+        const QkvEpi& e = p.qkv;
+        const bool gen = row_ok && e.expert != nullptr && e.qw1 != nullptr && e.expert[out_row];
+        const long long kv_row = (row_ok && e.kv_rows != nullptr) ? (long long)e.kv_rows[out_row] : out_row;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int head = n_blk * 2 + hh;
+          float x[128];
+          {
+            uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_x32(t_acc + hh * 128 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&xr[c * 32]));
+            tmem_ld_wait();
+          }
+          if (!row_ok) continue;
+          // q/k/v_proj output as the reference sees it: bf16(acc + bias)
+          const __nv_bfloat16* bh = p.bias + head * 128;
+#pragma unroll
+          for (int i = 0; i < 128; i += 2) {
+            const uint32_t bb = *reinterpret_cast<const uint32_t*>(bh + i);
+            x[i] = bf16_round(x[i] + bf16_lo(bb));
+            x[i + 1] = bf16_round(x[i + 1] + bf16_hi(bb));
+          }
+          __nv_bfloat16* dst;
+          const bool is_v = head >= e.Hq + e.Hk;
+          if (head < e.Hq) dst = e.q_out + out_row * e.ld_q + head * 128;
+          else if (!is_v) dst = e.k_out + kv_row * e.ld_kv + (head - e.Hq) * 128;
+          else dst = e.v_out + kv_row * e.ld_kv + (head - e.Hq - e.Hk) * 128;
+          if (!is_v) {
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 128; ++i) ss += x[i] * x[i];
+            const float r = rsqrtf(ss * (1.0f / 128.0f) + e.eps);
+            const __nv_bfloat16* w = (head < e.Hq) ? (gen ? e.qw1 : e.qw0) : (gen ? e.kw1 : e.kw0);
+            const float* cs = e.cos_t + out_row * 64;
+            const float* sn = e.sin_t + out_row * 64;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cs + i);
+              const float4 s4 = *reinterpret_cast<const float4*>(sn + i);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float wa = __bfloat162float(w[i + u]), wb = __bfloat162float(w[64 + i + u]);
+                float ya, yb, oa, ob;
+                if (e.fp32_flow) {
+                  ya = __fmul_rn(wa, __fmul_rn(x[i + u], r));
+                  yb = __fmul_rn(wb, __fmul_rn(x[64 + i + u], r));
+                  oa = __fadd_rn(__fmul_rn(ya, cc[u]), __fmul_rn(-yb, sv[u]));
+                  ob = __fadd_rn(__fmul_rn(yb, cc[u]), __fmul_rn(ya, sv[u]));
+                } else {
+                  ya = bf16_round(wa * bf16_round(x[i + u] * r));
+                  yb = bf16_round(wb * bf16_round(x[64 + i + u] * r));
+                  oa = bf16_round(ya * cc[u]) + bf16_round(-yb * sv[u]);
+                  ob = bf16_round(yb * cc[u]) + bf16_round(ya * sv[u]);
+                }
+                x[i + u] = oa;
+                x[64 + i + u] = ob;
+              }
+            }
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            d4[q] = make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                               pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+        }
+      } else if constexpr (EPI == EPI_SWIGLU) {
         const int n_out0 = n_blk * (BN / 2);
         __nv_bfloat16* crow = p.C + out_row * p.ldc + n_out0;
 #pragma unroll 1
@@ -467,4 +552,40 @@ extern "C" int bagel_conv2d_nhwc_bf16(const void* x, int B, int Hi, int Wi, int 
   if (bn == 256) return res ? launch_gemm<256, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<256, EPI_BIAS, true>(tmA, tmB, p, s);
   if (bn == 128) return res ? launch_gemm<128, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<128, EPI_BIAS, true>(tmA, tmB, p, s);
   return res ? launch_gemm<64, EPI_RESID, true>(tmA, tmB, p, s) : launch_gemm<64, EPI_BIAS, true>(tmA, tmB, p, s);
+}
+
+
+// QKV projection with the whole pre-attention tail fused into the epilogue (head_dim 128):
+//   [q|k|v] = A W^T + b ; per-head RMSNorm(q,k) with expert-routed weights ; RoPE ; bf16 ; q -> q_out,
+//   k/v -> merged KV buffers at kv_rows[row]. Replaces bagel_gemm_bf16 + bagel_qk_norm_rope (and the [N, 4608]
+//   round trip through HBM between them).
+extern "C" int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void* W, long long ldw, const void* bias,
+                                        int M, int K, const int* row_map, const void* q_w0, const void* k_w0,
+                                        const void* q_w1, const void* k_w1, const uint8_t* expert, const float* cos_t,
+                                        const float* sin_t, void* q_out, long long ld_q, void* k_out, void* v_out,
+                                        long long ld_kv, const int* kv_rows, int Hq, int Hk, float eps, int fp32_flow,
+                                        void* stream) {
+  const int N = (Hq + 2 * Hk) * 128;
+  if (M <= 0 || K <= 0 || Hq <= 0 || Hk <= 0) return set_error(BAGEL_ERR_SHAPE, "bagel_gemm_qkv_norm_rope: bad sizes");
+  if (N % 256) return set_error(BAGEL_ERR_SHAPE, "bagel_gemm_qkv_norm_rope: Hq + 2*Hk must be even (two heads per tile)");
+  if ((lda % 8) || (ldw % 8) || (K % 8) || (ld_q % 8) || (ld_kv % 8))
+    return set_error(BAGEL_ERR_ALIGN, "bagel_gemm_qkv_norm_rope: K and leading dims must be multiples of 8");
+  if (bias == nullptr || q_w0 == nullptr || k_w0 == nullptr || cos_t == nullptr || sin_t == nullptr)
+    return set_error(BAGEL_ERR_ARG, "bagel_gemm_qkv_norm_rope: bias, norm weights and RoPE tables are required");
+  if (int rc = require_sm100()) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.row_map = row_map;
+  p.qkv.qw0 = static_cast<const __nv_bfloat16*>(q_w0); p.qkv.kw0 = static_cast<const __nv_bfloat16*>(k_w0);
+  p.qkv.qw1 = static_cast<const __nv_bfloat16*>(q_w1); p.qkv.kw1 = static_cast<const __nv_bfloat16*>(k_w1);
+  p.qkv.expert = expert; p.qkv.cos_t = cos_t; p.qkv.sin_t = sin_t;
+  p.qkv.q_out = static_cast<__nv_bfloat16*>(q_out); p.qkv.k_out = static_cast<__nv_bfloat16*>(k_out);
+  p.qkv.v_out = static_cast<__nv_bfloat16*>(v_out);
+  p.qkv.ld_q = ld_q; p.qkv.ld_kv = ld_kv; p.qkv.kv_rows = kv_rows;
+  p.qkv.Hq = Hq; p.qkv.Hk = Hk; p.qkv.eps = eps; p.qkv.fp32_flow = fp32_flow;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, 256)) return rc;
+  return launch_gemm<256, EPI_QKV>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }

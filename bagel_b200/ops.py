@@ -96,8 +96,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
-def _i32(x: int) -> int:
-    return int(x)
+def gemm_qkv_norm_rope(a, w, bias, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk,
+                       eps: float, fp32_flow: bool, row_map=None):
+    """Fused QKV projection + per-head q/k RMSNorm + RoPE + bf16 cast + K/V placement (head_dim 128)."""
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    assert w.shape == ((Hq + 2 * Hk) * 128, K)
+    rc = _cabi.lib().bagel_gemm_qkv_norm_rope(
+        _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), M, K, _ptr(row_map), _ptr(q_w0), _ptr(k_w0),
+        _ptr(q_w1), _ptr(k_w1), _ptr(expert), _ptr(cos), _ptr(sin), _ptr(q_out), q_out.stride(0), _ptr(k_out),
+        _ptr(v_out), k_out.stride(0), _ptr(kv_rows), Hq, Hk, float(eps), int(fp32_flow), _stream())
+    _cabi.check(rc, "bagel_gemm_qkv_norm_rope")
 
 
 def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,

@@ -141,6 +141,7 @@ class Qwen2Model:
         self.device = torch.device(device)
         self.use_moe = "Mo" in config.layer_module
         self.enable_taylorseer = False
+        self.fused_qkv = True   # head_dim 128: q/k-norm + RoPE + KV placement fused into the QKV GEMM epilogue
         self.layers: List[_Layer] = [_Layer() for _ in range(config.num_hidden_layers)]
         self.embed_tokens: Optional[_Embedding] = None
         self.norm = None
@@ -215,13 +216,24 @@ class Qwen2Model:
             und = layer.und
             # ---- attention block ----
             ops.rmsnorm(xa, und.ln_in, main.ln_in if routed else None, plan.expert, eps, out=h)
-            ops.gemm(h, main.wqkv, bias=main.bqkv, out=qkv)
-            if nt:
-                ops.copy_rows(h, ht, src_rows=plan.text_rows)
-                ops.gemm(ht, und.wqkv, bias=und.bqkv, row_map=plan.text_rows, out=qkv)
-            ops.qk_norm_rope(qkv, und.q_norm, und.k_norm, main.q_norm if routed else None,
-                             main.k_norm if routed else None, plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li],
-                             plan.q_rows, Hq, Hk, D, eps, plan.fp32_flow)
+            if self.fused_qkv and D == 128:
+                # QKV GEMM with q/k-norm + RoPE + KV placement in its epilogue (no [n, 4608] round trip)
+                ops.gemm_qkv_norm_rope(h, main.wqkv, main.bqkv, und.q_norm, und.k_norm,
+                                       main.q_norm if routed else None, main.k_norm if routed else None, plan.expert,
+                                       plan.cos, plan.sin, q, kbuf[li], vbuf[li], plan.q_rows, Hq, Hk, eps, plan.fp32_flow)
+                if nt:
+                    ops.copy_rows(h, ht, src_rows=plan.text_rows)
+                    ops.gemm_qkv_norm_rope(ht, und.wqkv, und.bqkv, und.q_norm, und.k_norm, main.q_norm, main.k_norm,
+                                           plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li], plan.q_rows, Hq, Hk,
+                                           eps, plan.fp32_flow, row_map=plan.text_rows)
+            else:
+                ops.gemm(h, main.wqkv, bias=main.bqkv, out=qkv)
+                if nt:
+                    ops.copy_rows(h, ht, src_rows=plan.text_rows)
+                    ops.gemm(ht, und.wqkv, bias=und.bqkv, row_map=plan.text_rows, out=qkv)
+                ops.qk_norm_rope(qkv, und.q_norm, und.k_norm, main.q_norm if routed else None,
+                                 main.k_norm if routed else None, plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li],
+                                 plan.q_rows, Hq, Hk, D, eps, plan.fp32_flow)
             ops.attn_varlen(q.view(n, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), plan.cu_q, plan.cu_k,
                             plan.max_q, plan.max_k, plan.is_causal, out=att.view(n, Hq, D))
             ops.gemm(att, main.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)

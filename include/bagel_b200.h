@@ -59,6 +59,18 @@ int bagel_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
                     int N, int K, const void* bias, const void* resid, long long ldr, const int* row_map,
                     int epilogue, void* stream);
 
+/* QKV projection with the whole pre-attention tail fused into the GEMM epilogue (head_dim 128 only):
+ *   [q|k|v] = A W^T + bias; per-head RMSNorm of q and k with expert-routed weights; RoPE; bf16 cast; q -> q_out,
+ *   k / v -> merged KV buffers at row kv_rows[r]. One launch for bagel_gemm_bf16 + bagel_qk_norm_rope, without the
+ *   [M, (Hq+2Hk)*128] round trip through HBM (north_star: "RMSNorm+RoPE fused into the QKV projection epilogue";
+ *   reference modeling/bagel/qwen2_navit.py:515-557, 559-574). Arguments as in those two entry points; all per-row
+ *   tables (expert, cos_t, sin_t, kv_rows) are indexed by the OUTPUT row (row_map[r] when row_map is given). */
+int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void* W, long long ldw, const void* bias, int M, int K,
+                             const int* row_map, const void* q_w0, const void* k_w0, const void* q_w1, const void* k_w1,
+                             const uint8_t* expert, const float* cos_t, const float* sin_t, void* q_out, long long ld_q,
+                             void* k_out, void* v_out, long long ld_kv, const int* kv_rows, int Hq, int Hk, float eps,
+                             int fp32_flow, void* stream);
+
 /* Packed variable-length attention forward; same contract as flash_attn_varlen_func as the reference calls it
  * (modeling/bagel/qwen2_navit.py:361-370, 579-588; modeling/bagel/siglip_navit.py:232-241):
  *   q [total_q, Hq, D], k/v [total_k, Hk, D], out [total_q, Hq, D] bf16 (row strides ld_* in elements);

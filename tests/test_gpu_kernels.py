@@ -231,3 +231,46 @@ def test_loud_failure_on_bad_arguments():
     w = torch.zeros(16, 60, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(_cabi.BagelB200Error):
         ops.gemm(a, w)  # K not a multiple of 8
+
+
+@pytest.mark.parametrize("flow", [1, 0])
+def test_fused_qkv_epilogue_matches_two_kernel_path(flow):
+    """bagel_gemm_qkv_norm_rope == bagel_gemm_bf16 + bagel_qk_norm_rope (same rounding points; only the order of the
+    fp32 sum of squares differs), including the row_map scatter used for the und-expert rows."""
+    g = torch.Generator(device=DEV).manual_seed(77 + flow)
+    N, K, Hq, Hk, D = 700, 512, 6, 2, 128
+    a = torch.randn(N, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn((Hq + 2 * Hk) * D, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = (0.1 * torch.randn((Hq + 2 * Hk) * D, device=DEV, generator=g)).to(torch.bfloat16)
+    qw = [(1 + 0.1 * torch.randn(D, device=DEV, generator=g)).to(torch.bfloat16) for _ in range(2)]
+    kw = [(1 + 0.1 * torch.randn(D, device=DEV, generator=g)).to(torch.bfloat16) for _ in range(2)]
+    ex = (torch.rand(N, device=DEV, generator=g) > 0.3).to(torch.uint8)
+    pos = torch.randint(0, 5000, (N,), device=DEV, dtype=torch.int64, generator=g)
+    inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).to(DEV)
+    cos, sin = ops.rope_table(pos, inv_freq, True)
+    rows = torch.randperm(N + 40, device=DEV, generator=g)[:N].to(torch.int32)
+
+    def run(fused):
+        q = torch.zeros(N, Hq * D, device=DEV, dtype=torch.bfloat16)
+        kb = torch.zeros(N + 40, Hk * D, device=DEV, dtype=torch.bfloat16)
+        vb = torch.zeros_like(kb)
+        if fused:
+            ops.gemm_qkv_norm_rope(a, w, b, qw[0], kw[0], qw[1], kw[1], ex, cos, sin, q, kb, vb, rows, Hq, Hk, 1e-6, bool(flow))
+        else:
+            qkv = ops.gemm(a, w, bias=b)
+            ops.qk_norm_rope(qkv, qw[0], kw[0], qw[1], kw[1], ex, cos, sin, q, kb, vb, rows, Hq, Hk, D, 1e-6, bool(flow))
+        return q, kb, vb
+
+    q1, k1, v1 = run(True)
+    q0, k0, v0 = run(False)
+    assert torch.equal(v1, v0)
+    for got, ref in ((q1, q0), (k1, k0)):
+        _assert_bf16_close(got, ref, ulps=1.01, atol=4e-3)
+        assert (got != ref).float().mean().item() < 5e-3
+    # row_map variant: a few rows recomputed from a gathered A and scattered over their rows
+    sel = torch.tensor([0, 5, 699, 128, 129], device=DEV, dtype=torch.int32)
+    q2, k2, v2 = q1.clone(), k1.clone(), v1.clone()
+    q2[sel.long()] = 0
+    ops.gemm_qkv_norm_rope(a[sel.long()].contiguous(), w, b, qw[0], kw[0], qw[1], kw[1], ex, cos, sin, q2, k2, v2, rows, Hq, Hk,
+                           1e-6, bool(flow), row_map=sel)
+    assert torch.equal(q2, q1) and torch.equal(k2, k1) and torch.equal(v2, v1)
