@@ -10,6 +10,9 @@ from oracle import fixtures
 from oracle import vae as ov
 
 dev = "cuda"
+# torch baseline = the oracle's functional graph on the GPU with CUDA-autocast semantics (group_norm runs in fp32)
+import torch.nn.functional as F
+ov.gn = lambda sd, name, x: F.group_norm(x.float(), 32, sd[name + ".weight"], sd[name + ".bias"], eps=1e-6)
 def bench(fn, iters=3, warm=1):
     for _ in range(warm): fn()
     torch.cuda.synchronize()
@@ -29,6 +32,7 @@ for side in (512, 1024):
     img = torch.rand(1, 3, side, side, device=dev) * 2 - 1
     t_dec = bench(lambda: ae.decode(z))
     t_enc = bench(lambda: ae.encode(img))
+    print(f"[vae {side}^2 B=1] ours: decode {t_dec:.2f} ms, encode {t_enc:.2f} ms", flush=True)
     with torch.no_grad():
         t_dec_ref = bench(lambda: ov.decode(sd_gpu, vc, z))       # torch: cuDNN bf16 convs + ATen group_norm + SDPA
         t_enc_ref = bench(lambda: ov.encode(sd_gpu, vc, img))
