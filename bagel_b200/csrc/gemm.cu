@@ -495,6 +495,9 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
     bn = 256;
   } else {
     bn = (N % 256 == 0 || N >= 1024) ? 256 : (N > 64 ? 128 : 64);
+    // skinny M (text decode, und-expert rows of a MoT layer): the GEMM is a weight stream, so use narrow tiles to put
+    // 4x more CTAs (and TMA pipelines) on the W matrix
+    if (M <= BM && N >= 1024) bn = 64;
   }
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return rc;
