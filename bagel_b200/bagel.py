@@ -417,7 +417,7 @@ class Bagel:
         return nb
 
     def _cfg_update(self, st: Dict[str, Any], nb: int, scales: Tuple[float, float], renorm_min: float,
-                    renorm_type: str, x_dst: torch.Tensor, dt: float):
+                    renorm_type: str, x_dst: torch.Tensor, dt: float, dt_dev: Optional[torch.Tensor] = None):
         """CFG combine + renorm (bagel.py:873-905) fused with the Euler update x -= v*dt (:746)."""
         n, v = st["n"], st["v_all"]
         sT, sI = scales
@@ -425,7 +425,7 @@ class Bagel:
         v_img = v[2 * n:3 * n] if (nb >= 3 and sI > 1.0 and v_text is not None) else None
         ops.cfg_euler_step(v[:n], v_text, v_img, st["vae_rows"], x_dst, st["norms"],
                            sT if v_text is not None else 1.0, sI if v_img is not None else 1.0, renorm_min,
-                           renorm_type, dt)
+                           renorm_type, dt, dt_dev)
 
     def _flow_state(self, x_t, packed_seqlens, packed_vae_token_indexes, packed_text_indexes,
                     packed_vae_position_ids, packed_text_ids, nb: int) -> Dict[str, Any]:
@@ -592,21 +592,54 @@ class Bagel:
 
 
 class FlowRunner:
-    """A planned denoising run: x_t resident in HBM, one sync-free launch sequence per step."""
+    """A planned denoising run: x_t resident in HBM, one sync-free launch sequence per step. The per-step inputs
+    that change (timestep embedding row, dt) live in fixed device buffers, so the launch sequence of a step is
+    captured ONCE per branch set as a CUDA graph and replayed for the remaining steps."""
 
     def __init__(self, model: Bagel, st, dts, cfg_on, scales, renorm_min, renorm_type, nbmax, seqlens):
         self.model, self.st, self.dts, self.cfg_on = model, st, dts, cfg_on
         self.scales, self.renorm_min, self.renorm_type, self.nbmax = scales, renorm_min, renorm_type, nbmax
         self.seqlens = seqlens
         self.num_steps = len(dts)
+        dev = model.device
+        self.dts_dev = torch.tensor(dts, dtype=torch.float32, device=dev)
+        self.dt_cur = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.t_cur = torch.zeros_like(st["t_emb"][0])
+        self.use_cuda_graph = bool(getattr(model, "use_cuda_graph", True))
+        self._graphs: Dict[str, Any] = {}
+        self._eager_done: Dict[str, int] = {}
+
+    def _body(self, key: str):
+        m, st = self.model, self.st
+        on = key == "full"
+        nb = m._velocity(st, key, self.t_cur, st["x"])
+        m._cfg_update(st, nb, self.scales if on else (1.0, 1.0), self.renorm_min, self.renorm_type, st["x"], 0.0,
+                      self.dt_cur)
 
     @torch.no_grad()
     def step(self, i: int):
-        m, st = self.model, self.st
-        on = self.cfg_on[i] and self.nbmax > 1
-        nb = m._velocity(st, "full" if on else "main", st["t_emb"][i], st["x"])
-        m._cfg_update(st, nb, self.scales if on else (1.0, 1.0), self.renorm_min, self.renorm_type, st["x"],
-                      float(self.dts[i]))
+        key = "full" if (self.cfg_on[i] and self.nbmax > 1) else "main"
+        self.t_cur.copy_(self.st["t_emb"][i])
+        self.dt_cur.copy_(self.dts_dev[i:i + 1])
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            return
+        if self.use_cuda_graph and self._eager_done.get(key, 0) >= 1:
+            try:  # everything is warm (workspaces allocated, kernel attributes set): capture this step
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._body(key)
+                self._graphs[key] = graph
+                graph.replay()          # capture does not execute the work
+                return
+            except Exception as e:  # capture is an optimisation; the eager launch sequence is the same work
+                self.use_cuda_graph = False
+                import warnings
+                warnings.warn(f"bagel_b200: CUDA graph capture failed, continuing eagerly: {e}")
+                torch.cuda.synchronize()
+        self._body(key)
+        self._eager_done[key] = self._eager_done.get(key, 0) + 1
 
     def latents(self):
         return self.st["x"].split((self.seqlens - 2).tolist())

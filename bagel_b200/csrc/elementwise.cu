@@ -298,6 +298,7 @@ struct CfgArgs {
   float* norms;  // [2] fp32, zeroed by the caller before pass 1
   int M, C;
   float sT, sI, renorm_min, dt;
+  const float* dt_dev;  // optional: read dt from device memory (lets one CUDA graph serve every step)
   int renorm_type;
 };
 
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(128) cfg_apply_kernel(const CfgArgs a, int use
     sv += v * v;
     sw += w * w;
   }
+  const float dt = a.dt_dev ? *a.dt_dev : a.dt;
   float scale = gscale;
   if (use_cfg && a.renorm_type != 0) {
     sv = warp_sum(sv);
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(128) cfg_apply_kernel(const CfgArgs a, int use
       }
     }
     float* xp = a.x + (long long)r * a.C + c;
-    *xp = *xp - bf16_round(w * a.dt);
+    *xp = *xp - bf16_round(w * dt);
   }
 }
 
@@ -515,7 +517,8 @@ extern "C" int bagel_latent_embed_add(const void* proj, long long ldp, const voi
 
 extern "C" int bagel_cfg_euler_step(const void* v, const void* v_text, const void* v_img, long long ldv,
                                     const int* rows, float* x, float* norms_ws, int M, int C, float cfg_text_scale,
-                                    float cfg_img_scale, float renorm_min, int renorm_type, float dt, void* stream) {
+                                    float cfg_img_scale, float renorm_min, int renorm_type, float dt, const float* dt_dev,
+                                    void* stream) {
   if (M <= 0) return 0;
   if (C > 128) return set_error(BAGEL_ERR_SHAPE, "bagel_cfg_euler_step: C must be <= 128");
   if (renorm_type < 0 || renorm_type > 2) return set_error(BAGEL_ERR_ARG, "bagel_cfg_euler_step: renorm_type in {0,1,2}");
@@ -525,7 +528,8 @@ extern "C" int bagel_cfg_euler_step(const void* v, const void* v_text, const voi
   a.vT = static_cast<const __nv_bfloat16*>(v_text);
   a.vI = static_cast<const __nv_bfloat16*>(v_img);
   a.ldv = ldv; a.rows = rows; a.x = x; a.norms = norms_ws; a.M = M; a.C = C;
-  a.sT = cfg_text_scale; a.sI = cfg_img_scale; a.renorm_min = renorm_min; a.dt = dt; a.renorm_type = renorm_type;
+  a.sT = cfg_text_scale; a.sI = cfg_img_scale; a.renorm_min = renorm_min; a.dt = dt; a.dt_dev = dt_dev;
+  a.renorm_type = renorm_type;
   const int use_cfg = (cfg_text_scale > 1.0f && v_text != nullptr) ? 1 : 0;
   if (use_cfg && a.sI > 1.0f && a.vI == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_cfg_euler_step: cfg_img_scale > 1 needs v_img");
   if (use_cfg && renorm_type == 0) {

@@ -200,12 +200,13 @@ def latent_embed_add(proj, t_emb, pos_table, pos_ids, seq, dst_rows):
 RENORM = {"global": 0, "channel": 1, "text_channel": 2}
 
 
-def cfg_euler_step(v, v_text, v_img, rows, x, norms_ws, cfg_text_scale, cfg_img_scale, renorm_min, renorm_type, dt):
+def cfg_euler_step(v, v_text, v_img, rows, x, norms_ws, cfg_text_scale, cfg_img_scale, renorm_min, renorm_type, dt,
+                   dt_dev: Optional[torch.Tensor] = None):
     _req(x, torch.float32, "x")
     M, Cc = x.shape
     rc = _cabi.lib().bagel_cfg_euler_step(_ptr(v), _ptr(v_text), _ptr(v_img), v.stride(0), _ptr(rows), _ptr(x),
                                           _ptr(norms_ws), M, Cc, float(cfg_text_scale), float(cfg_img_scale),
-                                          float(renorm_min), RENORM[renorm_type], float(dt), _stream())
+                                          float(renorm_min), RENORM[renorm_type], float(dt), _ptr(dt_dev), _stream())
     _cabi.check(rc, "bagel_cfg_euler_step")
 
 

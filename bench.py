@@ -222,6 +222,9 @@ def main():
         cfg_text_past_key_values=ctxs["cfg_text"])
 
     # ---------------- device-resident timing: W warm-up + K timed denoising steps ----------------
+    # per-kernel CUDA-event timing (roofline) needs individually launched kernels: the device-resident region runs the
+    # launch sequence eagerly; the end-to-end region below replays it as a CUDA graph (the product default)
+    model.use_cuda_graph = False
     runner = model.make_flow_runner(past_key_values=ctxs["main"], **gen_input, **gen_kwargs)
     for i in range(args.warmup):
         runner.step(i % EVALS_PER_IMAGE)
@@ -289,6 +292,7 @@ def main():
 
     # ---------------- end to end through the public API ----------------
     e2e = None
+    model.use_cuda_graph = True
     if not args.no_e2e:
         noise_host = gen_input["packed_init_noises"].pin_memory()
         gi = dict(gen_input)

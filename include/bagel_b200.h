@@ -126,10 +126,12 @@ int bagel_latent_embed_add(const void* proj, long long ldp, const void* t_emb, c
 /* CFG combine + renorm + Euler update, x fp32 [M, C] in place (modeling/bagel/bagel.py:873-907, :746).
  *   v / v_text / v_img: bf16 llm2vae outputs of the main / text-dropped / image-dropped branches (row pitch ldv),
  *   latent token i lives at row rows[i] (NULL: i). v_text NULL or cfg_text_scale <= 1: plain x -= bf16(v*dt).
- *   renorm_type 0 "global" (needs norms_ws fp32[2]), 1 "channel", 2 "text_channel". */
+ *   renorm_type 0 "global" (needs norms_ws fp32[2]), 1 "channel", 2 "text_channel".
+ *   dt_dev: optional device pointer to the step size; when non-NULL it overrides `dt` (the same captured CUDA graph
+ *   can then be replayed for every step of a run). */
 int bagel_cfg_euler_step(const void* v, const void* v_text, const void* v_img, long long ldv, const int* rows,
                          float* x, float* norms_ws, int M, int C, float cfg_text_scale, float cfg_img_scale,
-                         float renorm_min, int renorm_type, float dt, void* stream);
+                         float renorm_min, int renorm_type, float dt, const float* dt_dev, void* stream);
 
 /* y[i] = bf16(x[i]) — the autocast cast in front of vae2llm (modeling/bagel/bagel.py:803). */
 int bagel_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);

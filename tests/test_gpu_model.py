@@ -295,3 +295,28 @@ def test_vit_tower_and_image_understanding_prefill(golden_dir):
     assert cache.key_cache[last].shape == g["vit.k_cache_last"].shape
     _check("vit ctx k", cache.key_cache[last], g["vit.k_cache_last"], None)
     _check("vit ctx v", cache.value_cache[last], g["vit.v_cache_last"], None)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(g_flow):
+    """generate_image captures the step's launch sequence once per branch set and replays it; results must equal the
+    eager launch sequence bit for bit (cfg_interval makes the run use both the 2-branch and the 1-branch graph)."""
+    cfg = fixtures.TINY_LM
+    model = helpers.build_product_bagel(cfg, "cuda")
+    ctx = _contexts(model, cfg)
+    c_main, kv_m, rp_m = ctx(True)
+    c_txt, kv_t, rp_t = ctx(False)
+    ct = model.prepare_vae_latent_cfg(kv_t, rp_t, helpers.IMAGE_SIZES)
+    outs = []
+    for use_graph in (False, True):
+        model.use_cuda_graph = use_graph
+        torch.manual_seed(2)
+        gi = model.prepare_vae_latent(kv_m, rp_m, helpers.IMAGE_SIZES, helpers.NEW_TOKEN_IDS)
+        lat = model.generate_image(
+            past_key_values=c_main, **gi, num_timesteps=9, timestep_shift=3.0, cfg_renorm_type="global",
+            cfg_interval=[0.4, 1.0], cfg_text_scale=3.0,
+            cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+            cfg_text_past_key_values=c_txt)
+        torch.cuda.synchronize()
+        outs.append(torch.cat(lat, 0).clone())
+    assert torch.equal(outs[0], outs[1])
