@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -62,13 +63,33 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&d);
 }
 
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 — P is rounded to bf16,
+// eps 3.9e-3, right after): the MUFU unit runs 16 ex2/clk/SM, i.e. 2048 cycles per pair of 128x128 score tiles — the
+// same as the four MMAs of that pair — so half of the exponentials are moved off it.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23: low mantissa bits = round(x)
+  const float2 t = fadd2(x, magic);
+  const float2 xi = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = ffma2(xi, make_float2(-1.0f, -1.0f), x);  // x - round(x) in [-0.5, 0.5]
+  float2 pz = ffma2(make_float2(0.05517147481441498f, 0.05517147481441498f), f, make_float2(0.242610901594162f, 0.242610901594162f));
+  pz = ffma2(pz, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  pz = ffma2(pz, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  // 2^round(x): add round(x) to the exponent field ((0x4B400000 + n) << 23 == n << 23 mod 2^32)
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-template <int D>
+template <int D, int kPolyMod>  // kPolyMod: every kPolyMod-th pair of exponentials runs on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -291,7 +312,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float2 x = ffma2(make_float2(s[c * 64 + 2 * i], s[c * 64 + 2 * i + 1]), sc2, nm2);
-            const float2 e = make_float2(ex2(x.x), ex2(x.y));
+            float2 e;
+            if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == (kPolyMod - 1)) e = ex2_poly2(x);
+            else e = make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
             pk[i] = pack_bf16x2(e.x, e.y);
           }
@@ -311,7 +334,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&o_bar[t], 0);
         tc_fence_after();
       }
-      const float inv_l = (l > 0.f) ? (1.f / l) : 0.f;
+      // rows that never saw a visible key (m still -inf) produce 0, as flash-attn does; the polynomial exp2 maps
+      // masked scores to 2^-126 instead of 0, which only matters for such rows
+      const float inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;
       const bool row_ok = qi < Lq;
       __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D;
 #pragma unroll
@@ -347,11 +372,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int D>
+template <int D, int kPolyMod>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
                        int B, int max_seqlen_q, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  auto kern = attn_varlen_kernel<D>;
+  auto kern = attn_varlen_kernel<D, kPolyMod>;
   static bool attr_done = false;
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -400,6 +425,16 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_dim == 128) return launch_attn<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-  return launch_attn<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  // BAGEL_ATTN_POLY = 0 (all exponentials on the MUFU), 2 (every 2nd pair on the FMA pipe, default), 3, 4: A/B knob
+  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 2; }();
+  if (head_dim == 128) {
+    switch (poly) {
+      case 0: return launch_attn<128, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+      case 3: return launch_attn<128, 3>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+      case 4: return launch_attn<128, 4>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+      default: return launch_attn<128, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+    }
+  }
+  return poly == 0 ? launch_attn<64, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
+                   : launch_attn<64, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
 }
