@@ -516,40 +516,124 @@ class Bagel:
     def generate_text(self, past_key_values: NaiveCache, packed_key_value_indexes, key_values_lens,
                       packed_start_tokens, packed_query_position_ids, max_length: int, do_sample: bool = False,
                       temperature: float = 1.0, end_token_id: Optional[int] = None):
-        """Greedy / sampled decode, one token per sample per step, KV appended (reference bagel.py:930-1000).
-        Returns [steps, B] token ids on the model's device. Like the reference, generation stops when SAMPLE 0
-        emits `end_token_id` (the reference supports batch 1 here, :996) and the stopping token is not returned.
-        Per-step index bookkeeping is done on the host in closed form (the reference rebuilds it with Python
-        loops over .tolist()); the LM call is the same packed `forward_inference(mode="und", is_causal=True)`."""
+        """Greedy / sampled decode, one token per sample per step (reference bagel.py:930-1000). Returns [steps, B]
+        token ids on the model's device. As in the reference, generation stops when SAMPLE 0 emits `end_token_id`
+        (:996) and the stopping token is not returned.
+
+        B200-first execution (the reference re-allocates and re-scatters the whole KV cache per layer per token and
+        rebuilds index tensors with host loops): the KV cache is copied ONCE into per-sample slabs with room for
+        `max_length` new tokens; sequence lengths, RoPE positions, write slots and the token history live on the
+        device; a step is embedding gather -> 28 layers (fused QKV epilogue appends K/V in place, attention reads
+        `seqused_k`) -> final norm -> lm_head -> argmax, captured once as a CUDA graph and replayed per token.
+        The only host<->device traffic per step is the 8-byte EOS check the reference also performs."""
         dev = self.device
+        lm = self.language_model.model
+        cfg = lm.config
+        L, H, Hq, Hk, D = cfg.num_hidden_layers, cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        w = Hk * D
         kv = torch.as_tensor(key_values_lens).to("cpu", torch.int64)
         B = int(kv.numel())
-        pos = torch.as_tensor(packed_query_position_ids).to("cpu", torch.int64).clone()
-        tokens = torch.as_tensor(packed_start_tokens).to(dev, torch.int64)
-        ones = torch.ones(B, dtype=torch.int32)
-        sample_ids = torch.arange(B, dtype=torch.int64)
-        out: List[torch.Tensor] = []
-        for _ in range(max_length):
-            out.append(tokens)
-            emb = self.language_model.model.embed_tokens(tokens)
-            # merged layout per sample: [cached_i | new token]; sample i starts at sum_{j<i}(kv_j + 1)
-            starts = torch.cumsum(kv + 1, 0) - (kv + 1)
-            res = self.language_model.forward_inference(
-                packed_query_sequence=emb, query_lens=ones, packed_query_position_ids=pos,
-                packed_query_indexes=starts + kv, past_key_values=past_key_values, key_values_lens=kv.to(torch.int32),
-                packed_key_value_indexes=_ranges(starts, kv), update_past_key_values=True, is_causal=True, mode="und")
-            past_key_values = res.past_key_values
-            logits = self.language_model.lm_head(res.packed_query_sequence)
-            if do_sample:
-                probs = torch.softmax(logits / temperature, dim=-1)
-                tokens = torch.multinomial(probs, num_samples=1).squeeze(1)
+        if max_length <= 0:
+            return torch.zeros((0, B), dtype=torch.int64, device=dev)
+        cap = kv + max_length
+        begin = torch.cumsum(cap, 0) - cap
+        total = int(cap.sum())
+        has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None and int(kv.sum()) > 0
+        kbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
+        vbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
+        if has_ctx:
+            n_ctx = int(kv.sum())
+            dst = _ranges(begin, kv).to(dev, torch.int32)
+            for li in range(L):
+                ops.copy_rows(past_key_values.key_cache[li].reshape(n_ctx, w), kbuf[li], dst_rows=dst, M=n_ctx)
+                ops.copy_rows(past_key_values.value_cache[li].reshape(n_ctx, w), vbuf[li], dst_rows=dst, M=n_ctx)
+        k_begin = torch.cat([begin, torch.tensor([total])]).to(dev, torch.int32)
+        cu_q = torch.arange(B + 1, dtype=torch.int32, device=dev)
+        seq_len = kv.to(dev, torch.int32)
+        pos = torch.as_tensor(packed_query_position_ids).to(dev, torch.int64).clone()
+        tokens = torch.as_tensor(packed_start_tokens).to(dev, torch.int64).clone()
+        tokens32 = tokens.to(torch.int32)
+        history = torch.zeros((max_length, B), dtype=torch.int64, device=dev)
+        step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        kv_rows = torch.zeros(B, dtype=torch.int32, device=dev)
+        seqused = torch.zeros(B, dtype=torch.int32, device=dev)
+        x = torch.empty((B, H), dtype=BF16, device=dev)
+        logits = torch.empty((B, cfg.vocab_size), dtype=BF16, device=dev)
+        eps = cfg.rms_norm_eps
+        bufs = dict(xb=torch.empty_like(x), h=torch.empty_like(x),
+                    qkv=torch.empty((B, (Hq + 2 * Hk) * D), dtype=BF16, device=dev),
+                    q=torch.empty((B, Hq * D), dtype=BF16, device=dev), att=torch.empty((B, Hq * D), dtype=BF16, device=dev),
+                    act=torch.empty((B, cfg.intermediate_size), dtype=BF16, device=dev), out=torch.empty_like(x))
+        head = self.language_model.lm_head
+
+        def body():
+            """One decode step; every input/output is a fixed device buffer (graph-replayable)."""
+            ops.copy_rows(lm.embed_tokens.weight, x, src_rows=tokens32, M=B)
+            cos, sin = bufs.get("cos"), bufs.get("sin")
+            ops.rope_table_into(pos, lm.inv_freq, cos, sin, True)
+            ops.decode_prepare(k_begin, seq_len, kv_rows, seqused)
+            xa, xb, h = x, bufs["xb"], bufs["h"]
+            for li, layer in enumerate(lm.layers):
+                e = layer.und
+                ops.rmsnorm(xa, e.ln_in, None, None, eps, out=h)
+                if lm.fused_qkv and D == 128:
+                    ops.gemm_qkv_norm_rope(h, e.wqkv, e.bqkv, e.q_norm, e.k_norm, None, None, None, cos, sin, bufs["q"],
+                                           kbuf[li], vbuf[li], kv_rows, Hq, Hk, eps, False)
+                else:
+                    ops.gemm(h, e.wqkv, bias=e.bqkv, out=bufs["qkv"])
+                    ops.qk_norm_rope(bufs["qkv"], e.q_norm, e.k_norm, None, None, None, cos, sin, bufs["q"], kbuf[li],
+                                     vbuf[li], kv_rows, Hq, Hk, D, eps, False)
+                ops.attn_varlen(bufs["q"].view(B, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), cu_q, k_begin,
+                                1, 0, True, out=bufs["att"].view(B, Hq, D), seqused_k=seqused)
+                ops.gemm(bufs["att"], e.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
+                ops.rmsnorm(xb, e.ln_post, None, None, eps, out=h)
+                ops.gemm(h, e.wgu, epilogue=ops.EPI_SWIGLU, out=bufs["act"])
+                ops.gemm(bufs["act"], e.wd, resid=xb, epilogue=ops.EPI_RESID, out=xa)
+            ops.rmsnorm(xa, lm.norm, None, None, eps, out=bufs["out"])
+            ops.gemm(bufs["out"], head.weight, bias=head.bias, out=logits)
+
+        def tail_greedy():
+            ops.decode_advance(seq_len, pos, tokens, history, step_dev)   # history[step] = current tokens; lens += 1
+            ops.argmax_rows(logits, tokens, tokens32)
+
+        bufs["cos"] = torch.empty((B, D // 2), dtype=torch.float32, device=dev)
+        bufs["sin"] = torch.empty((B, D // 2), dtype=torch.float32, device=dev)
+        graph = None
+        use_graph = bool(getattr(self, "use_cuda_graph", True)) and not do_sample
+        steps = 0
+        for step in range(max_length):
+            if graph is not None:
+                graph.replay()
             else:
-                tokens = torch.argmax(logits, dim=-1)
-            kv = kv + 1
-            pos = pos + 1
+                if use_graph and step == 1:
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            body()
+                            tail_greedy()
+                        graph = g
+                        graph.replay()
+                    except Exception as e:
+                        use_graph = False
+                        import warnings
+                        warnings.warn(f"bagel_b200: CUDA graph capture of the decode step failed, continuing eagerly: {e}")
+                        torch.cuda.synchronize()
+                        body()
+                        tail_greedy()
+                else:
+                    body()
+                    if do_sample:
+                        ops.decode_advance(seq_len, pos, tokens, history, step_dev)
+                        probs = torch.softmax(logits.float() / temperature, dim=-1)
+                        nxt = torch.multinomial(probs, num_samples=1).squeeze(1)
+                        tokens.copy_(nxt)
+                        tokens32.copy_(nxt.to(torch.int32))
+                    else:
+                        tail_greedy()
+            steps += 1
             if end_token_id is not None and int(tokens[0]) == end_token_id:
                 break
-        return torch.stack(out, dim=0)
+        return history[:steps].clone()
 
     @torch.no_grad()
     def _forward_flow(self, x_t, timestep, packed_vae_token_indexes, packed_vae_position_ids, packed_text_ids,

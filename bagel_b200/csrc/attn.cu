@@ -34,9 +34,11 @@ struct AttnParams {
   long long ld_out;  // elements between consecutive rows of out (= Hq*D for packed layout)
   const int* cu_q;   // [B+1]
   const int* cu_k;   // [B+1]
+  const int* seqused_k;  // optional [B]: keys in use per sample (<= cu_k[b+1]-cu_k[b]); KV buffers with spare capacity
   int Hq, Hk;
   int causal;
   float scale_log2;  // softmax_scale * log2(e)
+  long long* trace;  // debug: per-phase clock64 stamps of CTA (0,0,0) (BAGEL_ATTN_TRACE), else null
 };
 
 template <int D>
@@ -89,6 +91,8 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+#define ATTN_TRACE(slot) do { if (tr != nullptr) tr[(slot)] = clock64(); } while (0)
+
 template <int D, int kPolyMod>  // kPolyMod: every kPolyMod-th pair of exponentials runs on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -102,7 +106,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int b = blockIdx.z;
   const int h = blockIdx.y;
   const int q_beg = p.cu_q[b], Lq = p.cu_q[b + 1] - q_beg;
-  const int k_beg = p.cu_k[b], Lk = p.cu_k[b + 1] - k_beg;
+  const int k_beg = p.cu_k[b], Lk = p.seqused_k ? p.seqused_k[b] : (p.cu_k[b + 1] - k_beg);
   const int q0 = blockIdx.x * 2 * kBlockM;  // first query row (within the sample) of this CTA
   if (q0 >= Lq) return;                     // whole CTA idle (grid is sized by max_seqlen_q)
   const bool tile1_active = (q0 + kBlockM) < Lq;
@@ -231,12 +235,18 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tc_fence_after();
         for (int t = 0; t < ntile; ++t) {
+          long long* tr = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64)
+                              ? p.trace + 2ll * 64 * 8 + t * 4 : nullptr;
+          ATTN_TRACE(j * 8 + 0);
           mbar_wait(&p_bar[t], j & 1);  // P_t(j) in TMEM, O_t rescaled
           tc_fence_after();
+          ATTN_TRACE(j * 8 + 1);
           issue_pv(t, vstage, j > 0);
+          ATTN_TRACE(j * 8 + 2);
           if (!has_next) umma_commit(&o_bar[t]);
           // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
           if (has_next) issue_qk(t, kstage);
+          ATTN_TRACE(j * 8 + 3);
         }
         umma_commit(&kv_empty[vstage]);
         if (has_next) umma_commit(&kv_empty[kstage]);
@@ -255,15 +265,22 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (active) {
       float m = -INFINITY, l = 0.f;
+      // trace layout: [t][j][8] for softmax (slots 0..5), MMA uses [2][j][8] + t*4
+      long long* tr = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0)
+                          ? p.trace + (long long)t * 64 * 8 : nullptr;
       for (int j = 0; j < nblk; ++j) {
+        if (tr != nullptr && j >= 64) tr = nullptr;
+        ATTN_TRACE(j * 8 + 0);
         mbar_wait(&s_bar[t], j & 1);
         tc_fence_after();
+        ATTN_TRACE(j * 8 + 1);
         // registers written by tcgen05.ld may only be read after wait::ld
         uint32_t sr[kBlockN];
 #pragma unroll
         for (int c = 0; c < kBlockN / 32; ++c)
           tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
         tmem_ld_wait();
+        ATTN_TRACE(j * 8 + 2);
         float* s = reinterpret_cast<float*>(sr);
 
         const int kv0 = j * kBlockN;
@@ -301,6 +318,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_st_x32(tO + c * 32, v);
           }
         }
+        ATTN_TRACE(j * 8 + 3);
         const float neg_ms = -m_use * p.scale_log2;
         // x*scale - m*scale as packed f32x2 FMAs (Blackwell FFMA2: half the FMA-pipe issue slots), exp2 on the MUFU,
         // four independent partial row sums (packed adds) instead of one serial chain
@@ -323,10 +341,12 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
         m = m_new;
+        ATTN_TRACE(j * 8 + 4);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_bar[t]);
+        ATTN_TRACE(j * 8 + 5);
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
@@ -397,7 +417,7 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
                                      const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
                                      int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,
                                      float softmax_scale, long long ld_q, long long ld_k, long long ld_v,
-                                     long long ld_out, void* stream) {
+                                     long long ld_out, const int* seqused_k, void* stream) {
   (void)max_seqlen_k;
   if (head_dim != 64 && head_dim != 128)
     return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: head_dim must be 64 or 128 (got %d)", head_dim);
@@ -420,10 +440,13 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.ld_out = ld_out;
   p.cu_q = cu_seqlens_q;
   p.cu_k = cu_seqlens_k;
+  p.seqused_k = seqused_k;
   p.Hq = num_heads_q;
   p.Hk = num_heads_k;
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.trace = nullptr;
+  if (const char* e = getenv("BAGEL_ATTN_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // debug only
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // BAGEL_ATTN_POLY = 0 (all exponentials on the MUFU), 2 (every 2nd pair on the FMA pipe, default), 3, 4: A/B knob
   static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 2; }();

@@ -402,6 +402,61 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// text decode bookkeeping (bagel.py:945-992) kept on the device
+// ---------------------------------------------------------------------------------------------
+__global__ void decode_prepare_kernel(const int* __restrict__ k_begin, const int* __restrict__ seq_len,
+                                      int* __restrict__ kv_rows, int* __restrict__ seqused, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    kv_rows[b] = k_begin[b] + seq_len[b];
+    seqused[b] = seq_len[b] + 1;
+  }
+}
+
+__global__ void decode_advance_kernel(int* __restrict__ seq_len, long long* __restrict__ pos,
+                                      const long long* __restrict__ tokens, long long* __restrict__ history,
+                                      int* __restrict__ step_dev, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int step = step_dev[0];
+  if (b < B) {
+    seq_len[b] += 1;
+    pos[b] += 1;
+    history[(long long)step * B + b] = tokens[b];
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) step_dev[0] = step + 1;  // single block launch (B <= 1024)
+}
+
+// one block per row: first index of the maximum (torch.argmax tie rule)
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int V, long long* __restrict__ tokens,
+                   int* __restrict__ tokens32) {
+  const __nv_bfloat16* row = logits + (long long)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = __bfloat162float(row[i]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    tokens[blockIdx.x] = bi;
+    if (tokens32) tokens32[blockIdx.x] = bi;
+  }
+}
+
 }  // namespace bagel
 
 using namespace bagel;
@@ -552,6 +607,37 @@ extern "C" int bagel_cast_f32_to_bf16(const float* x, void* y, long long n, void
   if (n <= 0) return 0;
   cast_f32_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(y), n);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" int bagel_decode_prepare(const int* k_begin, const int* seq_len, int* kv_rows, int* seqused, int B,
+                                    void* stream) {
+  if (B <= 0) return 0;
+  decode_prepare_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(k_begin, seq_len, kv_rows, seqused, B);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_argmax_rows_bf16(const void* logits, long long ld, int B, int V, long long* tokens, int* tokens32,
+                                      void* stream) {
+  if (B <= 0 || V <= 0) return 0;
+  argmax_rows_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(logits), ld, V,
+                                                                       tokens, tokens32);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_decode_advance(int* seq_len, long long* pos, const long long* tokens, long long* history,
+                                    int* step_dev, int B, void* stream) {
+  if (B <= 0) return 0;
+  if (B > 1024) return set_error(BAGEL_ERR_SHAPE, "bagel_decode_advance: B must be <= 1024");
+  decode_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream)>>>(seq_len, pos, tokens, history,
+                                                                                          step_dev, B);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;

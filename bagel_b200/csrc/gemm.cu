@@ -78,7 +78,7 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -497,7 +497,7 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
     bn = (N % 256 == 0 || N >= 1024) ? 256 : (N > 64 ? 128 : 64);
     // skinny M (text decode, und-expert rows of a MoT layer): the GEMM is a weight stream, so use narrow tiles to put
     // 4x more CTAs (and TMA pipelines) on the W matrix
-    if (M <= BM && N >= 1024) bn = 64;
+    if (M <= BM && N >= 1024) bn = (N <= 8192) ? 32 : 64;  // >= 112 CTAs on the 3584/4608-wide projections
   }
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return rc;
@@ -506,6 +506,7 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   if (epilogue == EPI_SWIGLU) return launch_gemm<256, EPI_SWIGLU>(tmA, tmB, p, s);
   if (bn == 256) return dispatch_epi<256>(epilogue, tmA, tmB, p, s);
   if (bn == 128) return dispatch_epi<128>(epilogue, tmA, tmB, p, s);
+  if (bn == 32) return dispatch_epi<32>(epilogue, tmA, tmB, p, s);
   return dispatch_epi<64>(epilogue, tmA, tmB, p, s);
 }
 

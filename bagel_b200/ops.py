@@ -126,7 +126,7 @@ def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q:
     rc = _cabi.lib().bagel_attn_varlen_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(cu_seqlens_q), _ptr(cu_seqlens_k),
                                            Sq, Sk, B, Hq, Hk, D, int(max_seqlen_q), int(max_seqlen_k), int(bool(causal)),
                                            float(softmax_scale), q.stride(0), k.stride(0), v.stride(0), out.stride(0),
-                                           _stream())
+                                           _ptr(seqused_k), _stream())
     _cabi.check(rc, "bagel_attn_varlen_fwd")
     return out
 
@@ -164,6 +164,13 @@ def rope_table(pos: torch.Tensor, inv_freq: torch.Tensor, round_bf16: bool = Tru
     rc = _cabi.lib().bagel_rope_table(_ptr(pos), _ptr(inv_freq), _ptr(cos), _ptr(sin), N, half, int(round_bf16), _stream())
     _cabi.check(rc, "bagel_rope_table")
     return cos, sin
+
+
+def rope_table_into(pos: torch.Tensor, inv_freq: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, round_bf16: bool = True):
+    """rope_table writing into caller-owned buffers (graph-replayable decode step)."""
+    rc = _cabi.lib().bagel_rope_table(_ptr(pos), _ptr(inv_freq), _ptr(cos), _ptr(sin), pos.numel(), inv_freq.numel(),
+                                      int(round_bf16), _stream())
+    _cabi.check(rc, "bagel_rope_table")
 
 
 def qk_norm_rope(qkv, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D,
@@ -296,3 +303,24 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
     rc = _cabi.lib().bagel_transpose_bf16(_ptr(x), x.stride(0), _ptr(y), y.stride(0), R, Cc, _stream())
     _cabi.check(rc, "bagel_transpose_bf16")
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# text decode bookkeeping (device-resident)
+# ---------------------------------------------------------------------------------------------------------
+def decode_prepare(k_begin, seq_len, kv_rows, seqused):
+    rc = _cabi.lib().bagel_decode_prepare(_ptr(k_begin), _ptr(seq_len), _ptr(kv_rows), _ptr(seqused), seq_len.numel(), _stream())
+    _cabi.check(rc, "bagel_decode_prepare")
+
+
+def argmax_rows(logits: torch.Tensor, tokens: torch.Tensor, tokens32: Optional[torch.Tensor] = None):
+    _req(logits, torch.bfloat16, "logits"); _req(tokens, torch.int64, "tokens")
+    B, V = logits.shape
+    rc = _cabi.lib().bagel_argmax_rows_bf16(_ptr(logits), logits.stride(0), B, V, _ptr(tokens), _ptr(tokens32), _stream())
+    _cabi.check(rc, "bagel_argmax_rows_bf16")
+
+
+def decode_advance(seq_len, pos, tokens, history, step_dev):
+    rc = _cabi.lib().bagel_decode_advance(_ptr(seq_len), _ptr(pos), _ptr(tokens), _ptr(history), _ptr(step_dev),
+                                          seq_len.numel(), _stream())
+    _cabi.check(rc, "bagel_decode_advance")

@@ -77,12 +77,14 @@ int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void* W, long l
  *   cu_seqlens_q / cu_seqlens_k int32 [batch+1] DEVICE arrays; Hq % Hk == 0 (GQA); D in {64, 128};
  *   causal != 0: bottom-right aligned mask (query i sees keys <= i + Lk - Lq), as flash-attn >= 2.1;
  *   softmax in fp32, scale = softmax_scale (reference default D^-0.5). max_seqlen_q sizes the grid (host int,
- *   exactly what the reference passes); max_seqlen_k is accepted for signature parity and unused. */
+ *   exactly what the reference passes); max_seqlen_k is accepted for signature parity and unused.
+ *   seqused_k (optional int32[batch], device): number of keys in use per sample when the K/V rows of sample b start at
+ *   cu_seqlens_k[b] but the buffer has spare capacity (append-in-place decode; same meaning as flash-attn's seqused_k). */
 int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,
                           const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
                           int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,
                           float softmax_scale, long long ld_q, long long ld_k, long long ld_v, long long ld_out,
-                          void* stream);
+                          const int* seqused_k, void* stream);
 
 /* y = bf16(w_e * bf16(x * rsqrt(mean(x^2) + eps))), e = expert[row] ? w1 : w0 (expert / w1 may be NULL).
  * Qwen2RMSNorm (modeling/qwen2/modeling_qwen2.py:54-59) with the MoT row routing of
@@ -165,6 +167,17 @@ int bagel_softmax_rows_f32(const float* S, long long lds, void* P, long long ldp
 
 /* y[c, r] = x[r, c], bf16 (V^T for the P*V GEMM of the VAE mid attention). */
 int bagel_transpose_bf16(const void* x, long long ldx, void* y, long long ldy, int R, int C, void* stream);
+
+/* Text decode helpers (modeling/bagel/bagel.py:930-1000, one token per sample per step, all state on the device so a
+ * whole decode step is one replayable CUDA graph):
+ *   bagel_decode_prepare: kv_rows[b] = k_begin[b] + seq_len[b] (slot of the new token), seqused[b] = seq_len[b] + 1;
+ *   bagel_argmax_rows_bf16: tokens[b] = argmax_v logits[b, v] (first maximum, like torch.argmax), int64 out, and the
+ *     same ids as int32 (row indices for the next embedding gather);
+ *   bagel_decode_advance: seq_len[b] += 1; pos[b] += 1; history[step_dev[0], b] = tokens[b]; step_dev[0] += 1. */
+int bagel_decode_prepare(const int* k_begin, const int* seq_len, int* kv_rows, int* seqused, int B, void* stream);
+int bagel_argmax_rows_bf16(const void* logits, long long ld, int B, int V, long long* tokens, int* tokens32, void* stream);
+int bagel_decode_advance(int* seq_len, long long* pos, const long long* tokens, long long* history, int* step_dev, int B,
+                         void* stream);
 
 #ifdef __cplusplus
 }

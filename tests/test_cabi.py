@@ -22,7 +22,7 @@ def test_header_and_bindings_agree(lib):
 
 
 def test_abi_version_and_counters(lib):
-    assert lib.bagel_abi_version() == 1
+    assert lib.bagel_abi_version() == 2
     assert lib.bagel_launch_count() >= 0
     assert isinstance(lib.bagel_last_error(), bytes)
 
@@ -43,7 +43,7 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.bagel_gemm_bf16(None, 63, None, 64, None, 64, 8, 16, 64, None, None, 0, None, 0, None)
     assert rc == -2
     rc = lib.bagel_attn_varlen_fwd(None, None, None, None, None, None, 8, 8, 1, 4, 2, 96, 8, 8, 0, 1.0, 384, 192,
-                                   192, 384, None)
+                                   192, 384, None, None)
     assert rc == -1 and b"head_dim" in lib.bagel_last_error()
 
 
