@@ -301,10 +301,20 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 8; i < kBlockN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
         const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                                fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        const float m_new = fmaxf(m, mx);
+        // Lazy rescaling: `m` is the reference maximum the exponentials are taken against. It only moves (and O / l
+        // get rescaled) when the block maximum exceeds it by more than 2^kLazyLog2 in the exp2 domain; until then
+        // p = 2^((s - m) scale) may exceed 1 (bounded by 2^8 — harmless in fp32 sums and in bf16 P) and O, l stay
+        // consistent because both are accumulated against the same m. With one softmax thread per row, 32 rows per
+        // warp and a TMEM round trip per rescale, rescaling on every new maximum costs more than the softmax itself
+        // (profiles/r01_attn_timeline.txt).
+        constexpr float kLazyLog2 = 8.0f;
+        const float m_blk = fmaxf(m, mx);
+        const bool first = (m == -INFINITY);
+        const bool move = first ? (m_blk != -INFINITY) : ((m_blk - m) * p.scale_log2 > kLazyLog2);
+        const float m_new = move ? m_blk : m;
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = ex2((m - m_use) * p.scale_log2);  // m = -inf -> 0
-        const bool grow = (j > 0) && (m_new > m);
+        const float alpha = move ? ex2((m - m_use) * p.scale_log2) : 1.0f;  // m = -inf -> 0
+        const bool grow = (j > 0) && move;
         if (__any_sync(0xffffffffu, grow)) {
           // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order.
           const float a = grow ? alpha : 1.f;

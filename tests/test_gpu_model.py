@@ -320,3 +320,28 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(g_flow):
         torch.cuda.synchronize()
         outs.append(torch.cat(lat, 0).clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_generate_text_graph_vs_eager_and_eos(g_flow):
+    """The decode step replayed as a CUDA graph must produce the same ids as the eager launch sequence; generation
+    stops when sample 0 emits end_token_id and the stopping token is not returned (reference bagel.py:996)."""
+    from copy import deepcopy
+    cfg = fixtures.TINY_LM
+    model = helpers.build_product_bagel(cfg, "cuda")
+    c_main, kv_m, rp_m = _contexts(model, cfg)(True)
+    gs = model.prepare_start_tokens(kv_m, rp_m, helpers.NEW_TOKEN_IDS)
+    outs = []
+    for use_graph in (False, True):
+        model.use_cuda_graph = use_graph
+        outs.append(model.generate_text(past_key_values=deepcopy(c_main), max_length=10, do_sample=False, **gs).cpu())
+    assert torch.equal(outs[0], outs[1]) and outs[0].shape == (10, 2)
+    # stop on the token sample 0 produces at step 3 (history rows 0..3 are returned, the EOS itself is not)
+    eos = int(outs[0][4, 0])
+    first = next(i for i in range(1, 10) if int(outs[0][i, 0]) == eos)
+    short = model.generate_text(past_key_values=deepcopy(c_main), max_length=10, do_sample=False, end_token_id=eos, **gs).cpu()
+    assert short.shape[0] == first and torch.equal(short, outs[0][:first])
+    # the context handed in is not modified (gen_text deep-copies it anyway, inferencer.py:189)
+    snap = deepcopy(c_main)
+    model.generate_text(past_key_values=c_main, max_length=3, do_sample=True, temperature=0.7, **gs)
+    for li in range(cfg.num_hidden_layers):
+        assert torch.equal(snap.key_cache[li], c_main.key_cache[li])

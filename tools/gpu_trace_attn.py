@@ -9,8 +9,16 @@ torch.manual_seed(0)
 lq = [4098] * 16; lk = [4164] * 16
 q = torch.randn(sum(lq), 28, 128, device=dev).to(torch.bfloat16); k = torch.randn(sum(lk), 4, 128, device=dev).to(torch.bfloat16); v = torch.randn(sum(lk), 4, 128, device=dev).to(torch.bfloat16)
 cq = torch.tensor([0] + torch.tensor(lq).cumsum(0).tolist(), dtype=torch.int32, device=dev); ck = torch.tensor([0] + torch.tensor(lk).cumsum(0).tolist(), dtype=torch.int32, device=dev)
-for _ in range(2):
-    ops.attn_varlen(q, k, v, cq, ck, 4098, 4164, False)
+def bench(fn, iters=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+tt_ms = bench(lambda: ops.attn_varlen(q, k, v, cq, ck, 4098, 4164, False))
+print(f"BAGEL_ATTN_POLY={os.environ.get('BAGEL_ATTN_POLY','default')}: {tt_ms:.3f} ms = {4.0*16*4098*4164*28*128/tt_ms/1e9:.0f} TFLOP/s (with trace stores on CTA 0)")
 torch.cuda.synchronize()
 t = trace.cpu().reshape(3, 64, 8)
 t0 = int(t[t > 0].min())
