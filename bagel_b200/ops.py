@@ -111,7 +111,8 @@ def gemm_qkv_norm_rope(a, w, bias, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_o
 
 def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,
                 cu_seqlens_k: torch.Tensor, max_seqlen_q: int, max_seqlen_k: int, causal: bool = False,
-                softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+                seqused_k: Optional[torch.Tensor] = None) -> torch.Tensor:
     """flash_attn_varlen_func contract (qwen2_navit.py:579-588): q [Sq,Hq,D], k/v [Sk,Hk,D] bf16."""
     _req(q, torch.bfloat16, "q"); _req(k, torch.bfloat16, "k"); _req(v, torch.bfloat16, "v")
     _req(cu_seqlens_q, torch.int32, "cu_seqlens_q"); _req(cu_seqlens_k, torch.int32, "cu_seqlens_k")
