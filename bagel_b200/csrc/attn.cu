@@ -91,7 +91,15 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Timeline instrumentation (clock64 stamps of CTA (0,0,0)) is compiled in only with -DBAGEL_ATTN_TRACE_BUILD: even
+// dormant it costs registers in the softmax loop.
+#ifdef BAGEL_ATTN_TRACE_BUILD
 #define ATTN_TRACE(slot) do { if (tr != nullptr) tr[(slot)] = clock64(); } while (0)
+#define ATTN_TRACE_PTR(expr) (expr)
+#else
+#define ATTN_TRACE(slot) do { } while (0)
+#define ATTN_TRACE_PTR(expr) (nullptr)
+#endif
 
 template <int D, int kPolyMod>  // kPolyMod: every kPolyMod-th pair of exponentials runs on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -235,8 +243,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tc_fence_after();
         for (int t = 0; t < ntile; ++t) {
-          long long* tr = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64)
-                              ? p.trace + 2ll * 64 * 8 + t * 4 : nullptr;
+          [[maybe_unused]] long long* tr = ATTN_TRACE_PTR(
+              (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64)
+                  ? p.trace + 2ll * 64 * 8 + t * 4 : nullptr);
           ATTN_TRACE(j * 8 + 0);
           mbar_wait(&p_bar[t], j & 1);  // P_t(j) in TMEM, O_t rescaled
           tc_fence_after();
@@ -266,91 +275,132 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (active) {
       float m = -INFINITY, l = 0.f;
       // trace layout: [t][j][8] for softmax (slots 0..5), MMA uses [2][j][8] + t*4
-      long long* tr = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0)
-                          ? p.trace + (long long)t * 64 * 8 : nullptr;
+      [[maybe_unused]] long long* tr = ATTN_TRACE_PTR(
+          (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0)
+              ? p.trace + (long long)t * 64 * 8 : nullptr);
+      // Streamed online softmax. TMEM -> register reads run at ~64 B/clk per SM (a 128x128 fp32 S tile costs as many
+      // cycles as its two MMAs) and so does the MUFU for its 16K exponentials, so the two must overlap: S is read in
+      // 32-column chunks, and while chunk c+1 is in flight chunk c is exponentiated against the reference maximum `m`
+      // carried over from earlier blocks (lazy rescaling: p = 2^((s - m) scale) may reach 2^kLazyLog2, harmless in the
+      // fp32 row sum and in bf16 P). Only if the block maximum turns out to exceed m by more than the threshold
+      // (or no reference exists yet) is the block redone the classic way: move m, rescale O and l, re-read S.
+      constexpr float kLazyLog2 = 8.0f;
       for (int j = 0; j < nblk; ++j) {
+#ifdef BAGEL_ATTN_TRACE_BUILD
         if (tr != nullptr && j >= 64) tr = nullptr;
+#endif
         ATTN_TRACE(j * 8 + 0);
         mbar_wait(&s_bar[t], j & 1);
         tc_fence_after();
         ATTN_TRACE(j * 8 + 1);
-        // registers written by tcgen05.ld may only be read after wait::ld
-        uint32_t sr[kBlockN];
-#pragma unroll
-        for (int c = 0; c < kBlockN / 32; ++c)
-          tmem_ld_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
-        tmem_ld_wait();
-        ATTN_TRACE(j * 8 + 2);
-        float* s = reinterpret_cast<float*>(sr);
-
         const int kv0 = j * kBlockN;
         const int tile_q_lo = q0 + t * kBlockM;
         const bool need_mask = (kv0 + kBlockN > Lk) || (p.causal && (kv0 + kBlockN - 1 > tile_q_lo + shift));
-        if (need_mask) {
-          const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
-#pragma unroll
-          for (int i = 0; i < kBlockN; ++i)
-            if (kv0 + i > lim) s[i] = -INFINITY;
-        }
-        // 8 independent running maxima: a single serial fmax chain (128 dependent ops, 4-cycle latency each) is
-        // pure exposed latency with one softmax warp per scheduler
-        float mx8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = s[i];
-#pragma unroll
-        for (int i = 8; i < kBlockN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
-        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        // Lazy rescaling: `m` is the reference maximum the exponentials are taken against. It only moves (and O / l
-        // get rescaled) when the block maximum exceeds it by more than 2^kLazyLog2 in the exp2 domain; until then
-        // p = 2^((s - m) scale) may exceed 1 (bounded by 2^8 — harmless in fp32 sums and in bf16 P) and O, l stay
-        // consistent because both are accumulated against the same m. With one softmax thread per row, 32 rows per
-        // warp and a TMEM round trip per rescale, rescaling on every new maximum costs more than the softmax itself
-        // (profiles/r01_attn_timeline.txt).
-        constexpr float kLazyLog2 = 8.0f;
-        const float m_blk = fmaxf(m, mx);
-        const bool first = (m == -INFINITY);
-        const bool move = first ? (m_blk != -INFINITY) : ((m_blk - m) * p.scale_log2 > kLazyLog2);
-        const float m_new = move ? m_blk : m;
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = move ? ex2((m - m_use) * p.scale_log2) : 1.0f;  // m = -inf -> 0
-        const bool grow = (j > 0) && move;
-        if (__any_sync(0xffffffffu, grow)) {
-          // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order.
-          const float a = grow ? alpha : 1.f;
-#pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_x32(tO + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * a);
-            tmem_st_x32(tO + c * 32, v);
-          }
-        }
-        ATTN_TRACE(j * 8 + 3);
-        const float neg_ms = -m_use * p.scale_log2;
-        // x*scale - m*scale as packed f32x2 FMAs (Blackwell FFMA2: half the FMA-pipe issue slots), exp2 on the MUFU,
-        // four independent partial row sums (packed adds) instead of one serial chain
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_ms, neg_ms);
+        const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
+
+        uint32_t pk[kBlockN / 2];  // packed bf16 probabilities of the whole row (stored after S is fully read)
+        float mx = -INFINITY;
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+
+        // pass A: stream S, exponentiate against the current reference maximum
+        auto process = [&](const uint32_t (&v)[32], int c, float neg_ms, bool track_max) {
+          const float2 nm2 = make_float2(neg_ms, neg_ms);
+          float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < kBlockN / 64; ++c) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float2 x = ffma2(make_float2(s[c * 64 + 2 * i], s[c * 64 + 2 * i + 1]), sc2, nm2);
+          for (int i = 0; i < 16; ++i) {
+            float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
+            if (need_mask) {
+              if (kv0 + c * 32 + 2 * i > lim) x0 = -INFINITY;
+              if (kv0 + c * 32 + 2 * i + 1 > lim) x1 = -INFINITY;
+            }
+            if (track_max) cm[i & 3] = fmaxf(cm[i & 3], fmaxf(x0, x1));
+            const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
             float2 e;
             if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == (kPolyMod - 1)) e = ex2_poly2(x);
             else e = make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
-            pk[i] = pack_bf16x2(e.x, e.y);
+            pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
           }
-          tmem_st_x32(tS + c * 32, pk);
+          if (track_max) mx = fmaxf(mx, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        };
+
+        // warp-uniform (tcgen05.ld is .sync.aligned): the streamed path needs a reference maximum in every row of the warp
+        const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);
+        bool redo;
+        if (have_ref) {
+          const float neg_ms = -m * p.scale_log2;
+          uint32_t va[32], vb[32];
+          tmem_ld_x32(tS + 0, va);
+          tmem_ld_wait();
+          tmem_ld_x32(tS + 32, vb);
+          process(va, 0, neg_ms, true);
+          tmem_ld_wait();
+          tmem_ld_x32(tS + 64, va);
+          process(vb, 1, neg_ms, true);
+          tmem_ld_wait();
+          tmem_ld_x32(tS + 96, vb);
+          process(va, 2, neg_ms, true);
+          tmem_ld_wait();
+          process(vb, 3, neg_ms, true);
+          redo = (mx - m) * p.scale_log2 > kLazyLog2;
+        } else {
+          redo = true;
         }
+        ATTN_TRACE(j * 8 + 2);
+        float alpha = 1.0f;
+        if (__any_sync(0xffffffffu, redo)) {
+          // slow path (first block of a row, or a jump of the maximum): classic two-pass on a re-read of S,
+          // one 32-column chunk in registers at a time (rare, so latency matters less than register pressure)
+          if (!have_ref) {  // no pass A ran: find the block maximum first (warp-uniform: all rows start together)
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              tmem_ld_x32(tS + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(v[i]);
+                if (need_mask && (kv0 + c * 32 + i > lim)) x = -INFINITY;
+                mx = fmaxf(mx, x);
+              }
+            }
+          }
+          float neg_ms = -m * p.scale_log2;
+          if (redo) {
+            const float m_new = fmaxf(m, mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            alpha = ex2((m - m_use) * p.scale_log2);  // m = -inf -> 0
+            m = m_new;
+            neg_ms = -m_use * p.scale_log2;
+            rs2[0] = make_float2(0.f, 0.f);
+            rs2[1] = make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // all lanes load (sync.aligned); only the rows that moved recompute
+            uint32_t v[32];
+            tmem_ld_x32(tS + c * 32, v);
+            tmem_ld_wait();
+            if (redo) process(v, c, neg_ms, false);
+          }
+          if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld_x32(tO + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_x32(tO + c * 32, v);
+            }
+          }
+        }
+        ATTN_TRACE(j * 8 + 3);
         const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
-        m = m_new;
+        // P (bf16 pairs) over the first 64 columns of the S region: all of S has been read by now
+        tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+        tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
         ATTN_TRACE(j * 8 + 4);
         tmem_st_wait();
         tc_fence_before();
@@ -458,8 +508,9 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.trace = nullptr;
   if (const char* e = getenv("BAGEL_ATTN_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // debug only
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // BAGEL_ATTN_POLY = 0 (all exponentials on the MUFU), 2 (every 2nd pair on the FMA pipe, default), 3, 4: A/B knob
-  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 2; }();
+  // BAGEL_ATTN_POLY = 0 (all exponentials on the MUFU, default), 2/3/4 (every n-th pair on the FMA pipe): A/B knob —
+  // measured neutral-to-slower on B200 (profiles/r01_attn_poly_exp_ab.txt): the kernel is not MUFU-bound
+  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 0; }();
   if (head_dim == 128) {
     switch (poly) {
       case 0: return launch_attn<128, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
