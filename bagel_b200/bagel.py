@@ -538,6 +538,7 @@ class Bagel:
         cap = kv + max_length
         begin = torch.cumsum(cap, 0) - cap
         total = int(cap.sum())
+        max_kv = int(cap.max())   # host upper bound of any sample's key count (sizes the key split of decode attention)
         has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None and int(kv.sum()) > 0
         kbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
         vbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
@@ -576,7 +577,7 @@ class Bagel:
             for li, layer in enumerate(lm.layers):
                 e = layer.und
                 ops.rmsnorm(xa, e.ln_in, None, None, eps, out=h)
-                if lm.fused_qkv and D == 128:
+                if lm.fused_qkv and D == 128 and B > 64:   # B <= 64: weight-streaming skinny GEMM + norm/RoPE kernel
                     ops.gemm_qkv_norm_rope(h, e.wqkv, e.bqkv, e.q_norm, e.k_norm, None, None, None, cos, sin, bufs["q"],
                                            kbuf[li], vbuf[li], kv_rows, Hq, Hk, eps, False)
                 else:
@@ -584,7 +585,7 @@ class Bagel:
                     ops.qk_norm_rope(bufs["qkv"], e.q_norm, e.k_norm, None, None, None, cos, sin, bufs["q"], kbuf[li],
                                      vbuf[li], kv_rows, Hq, Hk, D, eps, False)
                 ops.attn_varlen(bufs["q"].view(B, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), cu_q, k_begin,
-                                1, 0, True, out=bufs["att"].view(B, Hq, D), seqused_k=seqused)
+                                1, max_kv, True, out=bufs["att"].view(B, Hq, D), seqused_k=seqused)
                 ops.gemm(bufs["att"], e.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
                 ops.rmsnorm(xb, e.ln_post, None, None, eps, out=h)
                 ops.gemm(h, e.wgu, epilogue=ops.EPI_SWIGLU, out=bufs["act"])

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "host_util.h"
+#include "attn_decode.h"
 
 namespace bagel {
 
@@ -478,7 +479,6 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
                                      int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,
                                      float softmax_scale, long long ld_q, long long ld_k, long long ld_v,
                                      long long ld_out, const int* seqused_k, void* stream) {
-  (void)max_seqlen_k;
   if (head_dim != 64 && head_dim != 128)
     return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: head_dim must be 64 or 128 (got %d)", head_dim);
   if (num_heads_k <= 0 || num_heads_q % num_heads_k)
@@ -488,6 +488,11 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
     return set_error(BAGEL_ERR_ALIGN, "bagel_attn_varlen_fwd: row strides %% 8 and 16-byte aligned pointers required");
   if (int rc = require_sm100()) return rc;
   if (total_q == 0 || max_seqlen_q <= 0) return 0;
+  // one query token per sample (text decode): HBM-bound split-KV kernel instead of the 128-row tcgen05 tiles.
+  // A single query sees every key under both mask settings (bottom-right aligned causal), so `causal` is moot.
+  if (attn_decode_supported(max_seqlen_q, head_dim, num_heads_q, num_heads_k))
+    return attn_decode(q, k, v, out, cu_seqlens_q, cu_seqlens_k, seqused_k, batch, num_heads_q, num_heads_k,
+                       max_seqlen_k, softmax_scale, ld_q, ld_k, ld_v, ld_out, static_cast<cudaStream_t>(stream));
 
   CUtensorMap tmQ, tmK, tmV;
   if (int rc = make_tmap_2d_bf16(&tmQ, q, (uint64_t)num_heads_q * head_dim, (uint64_t)total_q, (uint64_t)ld_q, 64, kBlockM)) return rc;

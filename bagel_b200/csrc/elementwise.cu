@@ -428,32 +428,54 @@ __global__ void decode_advance_kernel(int* __restrict__ seq_len, long long* __re
   if (blockIdx.x == 0 && threadIdx.x == 0) step_dev[0] = step + 1;  // single block launch (B <= 1024)
 }
 
-// one block per row: first index of the maximum (torch.argmax tie rule)
-__global__ void __launch_bounds__(256)
+// one block per row: first index of the maximum (torch.argmax tie rule). The row (vocab 152064 = 297 KB) was just
+// written by the lm_head GEMM and is L2-resident; 1024 threads x 16-byte loads keep ~16 KB per iteration in flight.
+constexpr int kArgmaxThreads = 1024;
+__global__ void __launch_bounds__(kArgmaxThreads)
 argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int V, long long* __restrict__ tokens,
                    int* __restrict__ tokens32) {
   const __nv_bfloat16* row = logits + (long long)blockIdx.x * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float v = __bfloat162float(row[i]);
+  auto take = [&](float v, int i) {
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  };
+  int vec_end = 0;
+  if ((ld % 8) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    vec_end = V & ~7;
+    for (int i = threadIdx.x * 8; i < vec_end; i += kArgmaxThreads * 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + i);
+      take(bf16_lo(u.x), i);     take(bf16_hi(u.x), i + 1);
+      take(bf16_lo(u.y), i + 2); take(bf16_hi(u.y), i + 3);
+      take(bf16_lo(u.z), i + 4); take(bf16_hi(u.z), i + 5);
+      take(bf16_lo(u.w), i + 6); take(bf16_hi(u.w), i + 7);
+    }
   }
+  for (int i = vec_end + threadIdx.x; i < V; i += kArgmaxThreads) take(__bfloat162float(row[i]), i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
-  __shared__ float sv[8];
-  __shared__ int si[8];
+  __shared__ float sv[kArgmaxThreads / 32];
+  __shared__ int si[kArgmaxThreads / 32];
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-    tokens[blockIdx.x] = bi;
-    if (tokens32) tokens32[blockIdx.x] = bi;
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x];
+    bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      if (bi == 0x7fffffff) bi = 0;   // all-NaN / all -inf row: torch returns an in-range index
+      tokens[blockIdx.x] = bi;
+      if (tokens32) tokens32[blockIdx.x] = bi;
+    }
   }
 }
 
@@ -625,7 +647,7 @@ extern "C" int bagel_decode_prepare(const int* k_begin, const int* seq_len, int*
 extern "C" int bagel_argmax_rows_bf16(const void* logits, long long ld, int B, int V, long long* tokens, int* tokens32,
                                       void* stream) {
   if (B <= 0 || V <= 0) return 0;
-  argmax_rows_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(logits), ld, V,
+  argmax_rows_kernel<<<B, kArgmaxThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(logits), ld, V,
                                                                        tokens, tokens32);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());

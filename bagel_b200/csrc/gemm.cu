@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "host_util.h"
+#include "gemm_skinny.h"
 
 namespace bagel {
 
@@ -488,6 +489,13 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   p.row_map = row_map;
   p.C32 = static_cast<float*>(C);  // used by BAGEL_EPI_F32 only (C is then an fp32 [M, ldc] buffer)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  if (epilogue == EPI_SWIGLU && (N % 256))
+    return set_error(BAGEL_ERR_SHAPE, "bagel_gemm_bf16: SwiGLU needs N (=2*I, interleaved) %% 256 == 0");
+  // token-by-token decode / und-expert text rows: weight-streaming kernel with swapped operands and cluster split-K
+  static const bool skinny_on = [] { const char* e = getenv("BAGEL_GEMM_SKINNY"); return !(e && atoi(e) == 0); }();
+  if (skinny_on && gemm_skinny_supported(M, N, K, epilogue))
+    return gemm_skinny(A, lda, W, ldw, C, ldc, M, N, K, bias, resid, ldr, row_map, epilogue, s);
 
   int bn;
   if (epilogue == EPI_SWIGLU) {

@@ -77,7 +77,8 @@ int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void* W, long l
  *   cu_seqlens_q / cu_seqlens_k int32 [batch+1] DEVICE arrays; Hq % Hk == 0 (GQA); D in {64, 128};
  *   causal != 0: bottom-right aligned mask (query i sees keys <= i + Lk - Lq), as flash-attn >= 2.1;
  *   softmax in fp32, scale = softmax_scale (reference default D^-0.5). max_seqlen_q sizes the grid (host int,
- *   exactly what the reference passes); max_seqlen_k is accepted for signature parity and unused.
+ *   exactly what the reference passes); max_seqlen_k (host int, <= 0 if unknown) only tunes the key split of the
+ *   single-query path: when max_seqlen_q == 1 (text decode, D = 128) a split-KV kernel streams the cache instead.
  *   seqused_k (optional int32[batch], device): number of keys in use per sample when the K/V rows of sample b start at
  *   cu_seqlens_k[b] but the buffer has spare capacity (append-in-place decode; same meaning as flash-attn's seqused_k). */
 int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,

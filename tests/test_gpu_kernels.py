@@ -69,6 +69,50 @@ def test_gemm_swiglu_gelu_silu():
     _assert_bf16_close(ops.gemm(a, gw, epilogue=ops.EPI_SILU), torch.nn.functional.silu(y), ulps=4.0)
 
 
+SKINNY_CASES = [  # (M, N, K): decode projections of the 7B model + ragged / tiny shapes (swapped-operand split-K kernel)
+    (1, 3584, 3584), (7, 4608, 3584), (16, 3584, 3584), (32, 3584, 18944), (33, 4608, 3584), (64, 3584, 3584),
+    (32, 152064, 512), (5, 264, 72), (32, 1024, 320), (24, 2048, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SKINNY_CASES)
+def test_gemm_skinny_bias_resid_rowmap(M, N, K):
+    """M <= 64 routes to gemm_skinny.cu (cluster split-K over DSMEM); same contract as the wide kernel."""
+    g = torch.Generator(device=DEV).manual_seed(M * 11 + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, generator=g).to(torch.bfloat16)
+    mm = _mm(a, w)
+    _assert_bf16_close(ops.gemm(a, w, bias=b), mm + b.float())
+    _assert_bf16_close(ops.gemm(a, w), mm)
+    res = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)
+    out = ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID)
+    _assert_bf16_close(out, res.float() + mm.to(torch.bfloat16).float(), scale_ref=res.float().abs() + mm.abs())
+    # deterministic: the split-K reduction order is fixed
+    assert torch.equal(out, ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID))
+    big = torch.zeros(200, N, device=DEV, dtype=torch.bfloat16)
+    rm = torch.randperm(200, device=DEV, generator=g)[:M].to(torch.int32)
+    ops.gemm(a, w, row_map=rm, out=big)
+    _assert_bf16_close(big[rm.long()], mm)
+    untouched = torch.ones(200, dtype=torch.bool, device=DEV)
+    untouched[rm.long()] = False
+    assert bool((big[untouched] == 0).all())
+
+
+@pytest.mark.parametrize("M,I,K", [(1, 18944, 3584), (32, 18944, 3584), (17, 512, 128), (64, 1024, 256)])
+def test_gemm_skinny_swiglu_gelu_silu(M, I, K):
+    g = torch.Generator(device=DEV).manual_seed(M + I)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    gw = (torch.randn(I, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    uw = (torch.randn(I, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    out = ops.gemm(a, ops.interleave_gate_up(gw, uw), epilogue=ops.EPI_SWIGLU)
+    ref = (torch.nn.functional.silu(_mm(a, gw).to(torch.bfloat16)) * _mm(a, uw).to(torch.bfloat16)).float()
+    _assert_bf16_close(out, ref, ulps=4.0)
+    y = _mm(a, gw).to(torch.bfloat16).float()
+    _assert_bf16_close(ops.gemm(a, gw, epilogue=ops.EPI_GELU), torch.nn.functional.gelu(y, approximate="tanh"), ulps=4.0)
+    _assert_bf16_close(ops.gemm(a, gw, epilogue=ops.EPI_SILU), torch.nn.functional.silu(y), ulps=4.0)
+
+
 def _ref_attn(q, k, v, lq, lk, causal):
     return om.varlen_attention(q.cpu(), k.cpu(), v.cpu(), lq, lk, causal)
 
@@ -94,6 +138,40 @@ def test_attn_varlen(lq, lk, Hq, Hk, D, causal):
     ref = _ref_attn(q, k, v, lq, lk, causal).float()
     ref = torch.nan_to_num(ref, nan=0.0)  # rows without any visible key: flash-attn returns 0
     torch.testing.assert_close(out.float().cpu(), ref, atol=2e-2, rtol=2e-2)
+
+
+DECODE_CASES = [  # (lens_k, Hq, Hk, spare rows per sample, q present per sample)
+    ([1245] * 8, 28, 4, 16, None), ([17, 300, 1, 5000], 28, 4, 0, None), ([33, 64, 127], 8, 8, 3, None),
+    ([700, 2, 129, 4097], 16, 4, 5, None), ([256, 31], 4, 2, 0, None), ([90, 0, 513], 8, 1, 2, None),
+    ([400, 77, 1300], 28, 4, 4, [1, 0, 1]),
+]
+
+
+@pytest.mark.parametrize("lk,Hq,Hk,spare,present", DECODE_CASES)
+def test_attn_decode_single_query(lk, Hq, Hk, spare, present):
+    """max_seqlen_q == 1 routes to the split-KV cluster kernel (attn_decode.cu): appended cache with spare capacity
+    (seqused_k), ragged lengths incl. empty caches and samples without a query; against the fp32 oracle."""
+    g = torch.Generator(device=DEV).manual_seed(sum(lk) + Hq)
+    B, D = len(lk), 128
+    present = present or [1] * B
+    cap = [n + spare for n in lk]
+    q = torch.randn(sum(present), Hq, D, device=DEV, generator=g).to(torch.bfloat16)
+    k = torch.randn(sum(cap), Hk, D, device=DEV, generator=g).to(torch.bfloat16)
+    v = torch.randn(sum(cap), Hk, D, device=DEV, generator=g).to(torch.bfloat16)
+    cq = torch.tensor([0] + torch.tensor(present).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    ck = torch.tensor([0] + torch.tensor(cap).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    used = torch.tensor(lk, dtype=torch.int32, device=DEV)
+    out = ops.attn_varlen(q, k, v, cq, ck, 1, max(lk), True, seqused_k=used)
+    begins = ck.tolist()
+    kd = torch.cat([k[begins[b]:begins[b] + lk[b]] for b in range(B)]).cpu()
+    vd = torch.cat([v[begins[b]:begins[b] + lk[b]] for b in range(B)]).cpu()
+    ref = om.varlen_attention(q.cpu(), kd, vd, present, lk, True).float()
+    ref = torch.nan_to_num(ref, nan=0.0)
+    torch.testing.assert_close(out.float().cpu(), ref, atol=1e-2, rtol=2e-2)
+    # deterministic merge order; unknown max_seqlen_k (<= 0) only changes the split, not the contract
+    assert torch.equal(out, ops.attn_varlen(q, k, v, cq, ck, 1, max(lk), True, seqused_k=used))
+    out2 = ops.attn_varlen(q, k, v, cq, ck, 1, 0, False, seqused_k=used)
+    torch.testing.assert_close(out2.float().cpu(), ref, atol=1e-2, rtol=2e-2)
 
 
 def test_attn_matches_flash_attn_semantics_at_model_shape():
@@ -274,3 +352,24 @@ def test_fused_qkv_epilogue_matches_two_kernel_path(flow):
     ops.gemm_qkv_norm_rope(a[sel.long()].contiguous(), w, b, qw[0], kw[0], qw[1], kw[1], ex, cos, sin, q2, k2, v2, rows, Hq, Hk,
                            1e-6, bool(flow), row_map=sel)
     assert torch.equal(q2, q1) and torch.equal(k2, k1) and torch.equal(v2, v1)
+
+
+@pytest.mark.parametrize("B,V", [(32, 152064), (3, 1000), (5, 8), (2, 4099)])
+def test_argmax_rows_first_max_index(B, V):
+    """Greedy token pick of generate_text (reference bagel.py:981 torch.argmax): bit-exact incl. the first-index tie
+    rule (bf16 logits tie often), on padded rows and odd vocab sizes."""
+    g = torch.Generator(device=DEV).manual_seed(V)
+    ld = ((V + 7) // 8) * 8 + 8
+    buf = torch.randn(B, ld, device=DEV, generator=g).to(torch.bfloat16)
+    logits = buf[:, :V]
+    top = logits.float().amax(1)
+    for b in range(B):                       # plant ties of the maximum at random places
+        idx = torch.randint(0, V, (3,), device=DEV, generator=g)
+        logits[b, idx] = top[b].to(torch.bfloat16)
+    buf[:, V:] = 1e4                         # padding beyond V must be ignored
+    tok = torch.empty(B, dtype=torch.int64, device=DEV)
+    tok32 = torch.empty(B, dtype=torch.int32, device=DEV)
+    ops.argmax_rows(logits, tok, tok32)
+    lf = logits.float()
+    first = (lf == lf.amax(1, keepdim=True)).float().argmax(1)   # first index of the maximum
+    assert torch.equal(tok, first) and torch.equal(tok32.long(), first)
