@@ -173,9 +173,11 @@ def forward_cache_update_text(sd, fc: FlowConfig, cache: KVCache, packed_text_id
 def forward_flow(sd, fc: FlowConfig, x_t, timestep, packed_vae_token_indexes, packed_vae_position_ids,
                  packed_text_ids, packed_text_indexes, packed_indexes, packed_position_ids, packed_seqlens,
                  key_values_lens, past_key_values, packed_key_value_indexes, cfg_renorm_min=0.0,
-                 cfg_renorm_type="global", cfg_text_scale=1.0, cfg_text=None, cfg_img_scale=1.0, cfg_img=None):
+                 cfg_renorm_type="global", cfg_text_scale=1.0, cfg_text=None, cfg_img_scale=1.0, cfg_img=None,
+                 taylor=None):
     """bagel.py:757-907. cfg_text / cfg_img: dicts with packed_position_ids, packed_query_indexes,
-    key_values_lens, past_key_values, packed_key_value_indexes of the respective branch."""
+    key_values_lens, past_key_values, packed_key_value_indexes of the respective branch.
+    taylor: None or (main, text, img) TaylorSeerState triple (bagel.py:680-684, 816-818, 836-838, 855-857)."""
     lsd = lm_sub(sd)
     H = fc.lm.hidden_size
     emb = F.embedding(packed_text_ids, sd["language_model.model.embed_tokens.weight"])
@@ -189,18 +191,20 @@ def forward_flow(sd, fc: FlowConfig, x_t, timestep, packed_vae_token_indexes, pa
         lat = lat.to(seq.dtype)
     seq[packed_vae_token_indexes] = lat
 
-    def branch(pos_ids, q_idx, kv_lens, cache, kv_idx):
+    def branch(pos_ids, q_idx, kv_lens, cache, kv_idx, ts_state=None):
         h, _ = om.lm_forward_inference(lsd, fc.lm, seq, packed_seqlens, pos_ids, q_idx, cache, kv_lens, kv_idx,
-                                       False, False, "gen", packed_vae_token_indexes, packed_text_indexes)
+                                       False, False, "gen", packed_vae_token_indexes, packed_text_indexes,
+                                       taylor=ts_state)
         return linear(h, sd["llm2vae.weight"], sd["llm2vae.bias"])[packed_vae_token_indexes]
 
-    v = branch(packed_position_ids, packed_indexes, key_values_lens, past_key_values, packed_key_value_indexes)
+    ts_main, ts_text, ts_img = taylor if taylor is not None else (None, None, None)
+    v = branch(packed_position_ids, packed_indexes, key_values_lens, past_key_values, packed_key_value_indexes, ts_main)
     if cfg_text_scale > 1.0:
         vT = branch(cfg_text["packed_position_ids"], cfg_text["packed_query_indexes"], cfg_text["key_values_lens"],
-                    cfg_text["past_key_values"], cfg_text["packed_key_value_indexes"])
+                    cfg_text["past_key_values"], cfg_text["packed_key_value_indexes"], ts_text)
     if cfg_img_scale > 1.0:
         vI = branch(cfg_img["packed_position_ids"], cfg_img["packed_query_indexes"], cfg_img["key_values_lens"],
-                    cfg_img["past_key_values"], cfg_img["packed_key_value_indexes"])
+                    cfg_img["past_key_values"], cfg_img["packed_key_value_indexes"], ts_img)
     if cfg_text_scale > 1.0:
         u = vT + cfg_text_scale * (v - vT)
         if cfg_renorm_type == "text_channel":
@@ -222,9 +226,14 @@ def forward_flow(sd, fc: FlowConfig, x_t, timestep, packed_vae_token_indexes, pa
 
 def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_timesteps=24, timestep_shift=1.0,
                    cfg_renorm_min=0.0, cfg_renorm_type="global", cfg_interval=(0, 1), cfg_text_scale=1.0,
-                   cfg_text=None, cfg_img_scale=1.0, cfg_img=None, trace: Optional[list] = None):
-    """bagel.py:644-754. gen_input = prepare_vae_latent(...) dict. Returns the tuple of per-sample latents."""
+                   cfg_text=None, cfg_img_scale=1.0, cfg_img=None, trace: Optional[list] = None,
+                   enable_taylorseer: bool = False):
+    """bagel.py:644-754. gen_input = prepare_vae_latent(...) dict. Returns the tuple of per-sample latents.
+    enable_taylorseer: one TaylorSeer cache per branch, created per call (bagel.py:680-684)."""
     x_t = gen_input["packed_init_noises"]
+    taylor = None
+    if enable_taylorseer:
+        taylor = tuple(om.TaylorSeerState(fc.lm.num_hidden_layers, num_timesteps) for _ in range(3))
     ts = torch.linspace(1, 0, num_timesteps)
     ts = timestep_shift * ts / (1 + (timestep_shift - 1) * ts)
     dts = ts[:-1] - ts[1:]
@@ -237,7 +246,7 @@ def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_tim
                          gen_input["packed_text_indexes"], gen_input["packed_indexes"],
                          gen_input["packed_position_ids"], gen_input["packed_seqlens"], gen_input["key_values_lens"],
                          past_key_values, gen_input["packed_key_value_indexes"], cfg_renorm_min, cfg_renorm_type,
-                         cfg_text_scale if on else 1.0, cfg_text, cfg_img_scale if on else 1.0, cfg_img)
+                         cfg_text_scale if on else 1.0, cfg_text, cfg_img_scale if on else 1.0, cfg_img, taylor=taylor)
         if trace is not None:
             trace.append(v.clone())
         x_t = x_t - v * dts[i]

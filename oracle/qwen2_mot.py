@@ -176,6 +176,60 @@ def _attention(x, sd, cfg: LMConfig, li: int, cos, sin, query_lens, packed_query
     return o
 
 
+class TaylorSeerState:
+    """Step-cache state of ONE velocity branch (main / text-CFG / image-CFG): restatement of
+    modeling/cache_utils/taylorseer.py — `cache_init` (:128-166: fresh_threshold 3, max_order 6, first_enhance 5,
+    taylor_cache True, fresh_ratio 0), `cal_type` (:80-122), `force_scheduler` (:62-76, linear_step_weight 0 =>
+    cal_threshold = round(3 / 1) = 3), `derivative_approximation` (:12-32), `taylor_formula` (:34-47) — as driven by
+    Qwen2Model.forward_inference (qwen2_navit.py:1034-1037, 1057-1061, 1086-1087) and the decoder layer
+    (qwen2_navit.py:773-777, 824-829). Every layer keeps its own factors exactly as the reference does, although on
+    a 'Taylor' step only the LAST layer's extrapolation reaches the output (each layer's result replaces its input)."""
+
+    def __init__(self, num_layers: int, num_steps: int):
+        self.factors: List[Dict[int, torch.Tensor]] = [dict() for _ in range(num_layers)]
+        self.cache_counter = 0
+        self.fresh_threshold = 3
+        self.cal_threshold = None
+        self.max_order = 6
+        self.first_enhance = 5
+        self.activated_steps = [0]
+        self.step = 0
+        self.num_steps = num_steps
+        self.type = None
+
+    def cal_type(self):
+        first = self.step < self.first_enhance
+        interval = self.fresh_threshold if first else self.cal_threshold
+        if first or self.cache_counter == interval - 1:
+            self.type = "full"
+            self.cache_counter = 0
+            self.activated_steps.append(self.step)
+            self.cal_threshold = int(round(self.fresh_threshold / 1.0))   # force_scheduler, step_factor == 1
+        else:
+            self.cache_counter += 1
+            self.type = "Taylor"
+
+    def derivative_approximation(self, layer: int, feature: torch.Tensor):
+        dist = self.activated_steps[-1] - self.activated_steps[-2]
+        old = self.factors[layer]
+        new = {0: feature}
+        for i in range(self.max_order):
+            if old.get(i, None) is not None and self.step > self.first_enhance - 2:
+                new[i + 1] = (new[i] - old[i]) / dist
+            else:
+                break
+        self.factors[layer] = new
+
+    def taylor_formula(self, layer: int):
+        import math
+        x = self.step - self.activated_steps[-1]
+        out = 0
+        f = self.factors[layer]
+        for i in range(len(f)):
+            out += (1 / math.factorial(i)) * f[i] * (x ** i)
+        return out
+
+
 def _layer(x, sd, cfg, li, cos, sin, mode, vae_idx, text_idx, **attn_kw):
     """qwen2_navit.py:757-831 (Qwen2MoTDecoderLayer.forward_inference, TaylorSeer off)."""
     p = f"model.layers.{li}."
@@ -205,15 +259,28 @@ def _layer(x, sd, cfg, li, cos, sin, mode, vae_idx, text_idx, **attn_kw):
 def lm_forward_inference(sd: Dict[str, torch.Tensor], cfg: LMConfig, packed_query_sequence, query_lens,
                          packed_query_position_ids, packed_query_indexes, past_key_values: Optional[KVCache] = None,
                          key_values_lens=None, packed_key_value_indexes=None, update_past_key_values=True,
-                         is_causal=True, mode="und", packed_vae_token_indexes=None, packed_text_indexes=None):
-    """qwen2_navit.py:1018-1092 (Qwen2Model.forward_inference). Returns (hidden [N,H], cache)."""
+                         is_causal=True, mode="und", packed_vae_token_indexes=None, packed_text_indexes=None,
+                         taylor: Optional["TaylorSeerState"] = None):
+    """qwen2_navit.py:1018-1092 (Qwen2Model.forward_inference). Returns (hidden [N,H], cache).
+    `taylor`: TaylorSeer state of the calling branch (enable_taylorseer=True), else None."""
     x = packed_query_sequence
+    if taylor is not None:
+        taylor.cal_type()
     cos, sin = rope_tables(packed_query_position_ids, cfg.head_dim, cfg.rope_theta, x.dtype)
     for li in range(cfg.num_hidden_layers):
-        x = _layer(x, sd, cfg, li, cos, sin, mode, packed_vae_token_indexes, packed_text_indexes,
-                   query_lens=query_lens, packed_query_indexes=packed_query_indexes, cache=past_key_values,
-                   key_values_lens=key_values_lens, packed_key_value_indexes=packed_key_value_indexes,
-                   update=update_past_key_values, is_causal=is_causal)
+        if taylor is not None and taylor.type == "full" and taylor.step == 0:
+            taylor.factors[li] = {}                                   # taylor_cache_init (:49-58)
+        if taylor is None or taylor.type == "full":
+            x = _layer(x, sd, cfg, li, cos, sin, mode, packed_vae_token_indexes, packed_text_indexes,
+                       query_lens=query_lens, packed_query_indexes=packed_query_indexes, cache=past_key_values,
+                       key_values_lens=key_values_lens, packed_key_value_indexes=packed_key_value_indexes,
+                       update=update_past_key_values, is_causal=is_causal)
+            if taylor is not None:
+                taylor.derivative_approximation(li, x)
+        else:
+            x = taylor.taylor_formula(li)
+    if taylor is not None:
+        taylor.step += 1
     eps = cfg.rms_norm_eps
     if mode == "und":
         x = rms_norm(x, sd["model.norm.weight"], eps)

@@ -202,6 +202,41 @@ def golden_flow(ns):
             assert torch.equal(a, b), f"oracle generate_image != reference ({name})"
         out[f"gen.{name}.latents"] = torch.cat(lat, dim=0).contiguous()
         print(f"generate_image[{name}]: oracle == reference (bit-exact); |x| mean {float(torch.cat(lat).abs().mean()):.4f}")
+    # ---- TaylorSeer step cache (enable_taylorseer=True, bagel.py:678-684; cache_utils/taylorseer.py): 14 timesteps =
+    # 13 evaluations -> full steps 0-4, 7, 10 (Taylor orders 1, 2, 3), extrapolated steps 5, 6, 8, 9, 11, 12; the CFG
+    # branches stop at the cfg_interval boundary with their own step counters ----
+    out_ts = {}
+    for name, sT, sI, rt in [("taylor_nocfg", 1.0, 1.0, "global"), ("taylor_global_img", 4.0, 1.5, "global"),
+                             ("taylor_text_channel", 4.0, 1.0, "text_channel")]:
+        kwargs = dict(num_timesteps=14, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type=rt,
+                      cfg_interval=[0.4, 1.0], cfg_text_scale=sT, cfg_img_scale=sI, enable_taylorseer=True)
+        ref_kw = dict(kwargs)
+        ref_kw.update(
+            cfg_text_packed_position_ids=cfg_t["cfg_packed_position_ids"],
+            cfg_text_packed_query_indexes=cfg_t["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=cfg_t["cfg_key_values_lens"],
+            cfg_text_packed_key_value_indexes=cfg_t["cfg_packed_key_value_indexes"],
+            cfg_text_past_key_values=rc_txt,
+            cfg_img_packed_position_ids=cfg_i["cfg_packed_position_ids"],
+            cfg_img_packed_query_indexes=cfg_i["cfg_packed_query_indexes"],
+            cfg_img_key_values_lens=cfg_i["cfg_key_values_lens"],
+            cfg_img_packed_key_value_indexes=cfg_i["cfg_packed_key_value_indexes"],
+            cfg_img_past_key_values=rc_img)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            lat = model.generate_image(past_key_values=rc_main, **gi, **ref_kw)
+        with torch.no_grad():
+            olat = obf.generate_image(sd_full, fc, ogi, oc_main, cfg_text=obranch(cfg_t, oc_txt),
+                                      cfg_img=obranch(cfg_i, oc_img), **kwargs)
+        for a, b in zip(lat, olat):
+            assert torch.equal(a, b), f"oracle generate_image != reference ({name})"
+        out_ts[f"gen.{name}.latents"] = torch.cat(lat, dim=0).contiguous()
+        print(f"generate_image[{name}]: oracle == reference (bit-exact); |x| mean {float(torch.cat(lat).abs().mean()):.4f}")
+    save_file(out_ts, os.path.join(OUT, "flow_taylor_tiny.safetensors"))
+    # the reference leaves the flag set on the model AND on every decoder layer after such a call (bagel.py:681,
+    # qwen2_navit.py:1060); a later non-TaylorSeer forward in the same process would then read the stale cache
+    model.language_model.model.enable_taylorseer = False
+    for layer in model.language_model.model.layers:
+        layer.enable_taylorseer = False
     # ---- greedy text decode on top of the text context (bagel.py:930-1000), 12 steps, B=2 ----
     from copy import deepcopy
     gs = model.prepare_start_tokens(kv_main, rp_main, NEW_TOKEN_IDS)

@@ -85,7 +85,10 @@ def test_packers_and_prefill_bit_exact(g_flow):
 
 @pytest.mark.parametrize("name,sT,sI,rt", [
     ("nocfg", 1.0, 1.0, "global"), ("global", 4.0, 1.0, "global"), ("channel", 4.0, 1.0, "channel"),
-    ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel")])
+    ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel"),
+    # TaylorSeer step cache (enable_taylorseer=True): 13 evaluations, full at 0-4/7/10, Taylor orders up to 3
+    ("taylor_nocfg", 1.0, 1.0, "global"), ("taylor_global_img", 4.0, 1.5, "global"),
+    ("taylor_text_channel", 4.0, 1.0, "text_channel")])
 def test_generate_image_bit_exact(g_flow, name, sT, sI, rt):
     cfg = fixtures.TINY_LM
     sd = helpers.flow_state_dict(cfg)
@@ -105,10 +108,13 @@ def test_generate_image_bit_exact(g_flow, name, sT, sI, rt):
                         packed_query_indexes=d["cfg_packed_query_indexes"], key_values_lens=d["cfg_key_values_lens"],
                         past_key_values=cache, packed_key_value_indexes=d["cfg_packed_key_value_indexes"])
 
-        lat = obf.generate_image(sd, fc, gi, c_main, num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0,
-                                 cfg_renorm_type=rt, cfg_interval=[0.4, 1.0], cfg_text_scale=sT,
-                                 cfg_text=br(kv_t, rp_t, c_txt), cfg_img_scale=sI, cfg_img=br(kv_i, rp_i, c_img))
-    assert torch.equal(torch.cat(lat, 0), g_flow[f"gen.{name}.latents"])
+        taylor = name.startswith("taylor_")
+        lat = obf.generate_image(sd, fc, gi, c_main, num_timesteps=14 if taylor else 4, timestep_shift=3.0,
+                                 cfg_renorm_min=0.0, cfg_renorm_type=rt, cfg_interval=[0.4, 1.0], cfg_text_scale=sT,
+                                 cfg_text=br(kv_t, rp_t, c_txt), cfg_img_scale=sI, cfg_img=br(kv_i, rp_i, c_img),
+                                 enable_taylorseer=taylor)
+    gold = load_file(os.path.join(os.path.dirname(__file__), "golden", "flow_taylor_tiny.safetensors")) if taylor else g_flow
+    assert torch.equal(torch.cat(lat, 0), gold[f"gen.{name}.latents"])
 
 
 def test_generate_text_greedy_bit_exact(g_flow):

@@ -3,6 +3,7 @@ argmax. Weights are cycled over NSETS distinct copies (each layer set is 466 MB 
 Usage: python tools/gpu_perf_decode_kernels.py [B] [ctx]"""
 import sys
 import torch
+sys.path.insert(0, ".")
 from bagel_b200 import ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32

@@ -40,10 +40,14 @@ ntok = sum(kv)
 print(f"[cfg3 und prefill] B={B}: {ntok} tokens ({ntok//B}/sample) in {dt*1e3:.1f} ms = {ntok/dt:.0f} tokens/s (incl. host packing, H2D of patches)", flush=True)
 
 gs = model.prepare_start_tokens(kv, rp, synthetic.NEW_TOKEN_IDS)
-for steps in (4, 16):
+times = {}
+for steps in (4, 16, 128):
     from copy import deepcopy
     c = deepcopy(cache); torch.cuda.synchronize()
     t0 = time.perf_counter(); toks = model.generate_text(past_key_values=c, max_length=steps, do_sample=False, **gs); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"[decode] B={B} ctx={ntok//B}: {steps} steps in {dt*1e3:.1f} ms = {dt/steps*1e3:.2f} ms/step = {B*steps/dt:.0f} tokens/s "
           f"(HBM roofline: ~14.1 GB weights/step -> 2.1 ms)", flush=True)
+    times[steps] = dt
+marg = (times[128] - times[16]) / 112
+print(f"[decode] steady state (marginal over steps 16..128, CUDA-graph replay): {marg*1e3:.2f} ms/step = {B/marg:.0f} tokens/s", flush=True)
