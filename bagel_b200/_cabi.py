@@ -47,6 +47,8 @@ SIGNATURES = {
     "bagel_upsample2x_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "bagel_softmax_rows_f32": (_i, [_vp, _ll, _vp, _ll, _i, _i, _f, _vp]),
     "bagel_transpose_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "bagel_taylor_update_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "bagel_taylor_eval_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _i, _vp]),
 }
 
 

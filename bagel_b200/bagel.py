@@ -399,9 +399,10 @@ class Bagel:
                 ops.copy_rows(cache.value_cache[li].reshape(m, w), vbuf[li], dst_rows=rows, M=m)
         return plan, kbuf, vbuf
 
-    def _velocity(self, st: Dict[str, Any], key: str, t_row: torch.Tensor, x_src: torch.Tensor) -> int:
+    def _velocity(self, st: Dict[str, Any], key: str, t_row: torch.Tensor, x_src: torch.Tensor, head: bool = True) -> int:
         """Latent-in (bagel.py:796-806) -> packed LM call over all CFG branches -> llm2vae (:832). Fills
-        st['v_all'][b*n:(b+1)*n] with branch b's outputs for every packed row; returns the branch count."""
+        st['v_all'][b*n:(b+1)*n] with branch b's outputs for every packed row; returns the branch count.
+        head=False stops after the last decoder layer (TaylorSeer caches / replaces that tensor)."""
         lm = self.language_model.model
         plan, kbuf, vbuf, nb = st[key]
         n = st["n"]
@@ -412,9 +413,17 @@ class Bagel:
             ops.latent_embed_add(st["proj"], t_row, self.latent_pos_embed.pos_embed, st["vae_pos"],
                                  seq[b * n:(b + 1) * n], st["vae_rows"])
             ops.copy_rows(st["text_emb"], seq[b * n:(b + 1) * n], dst_rows=st["text_rows"])
-        out = lm.run_layers(seq, plan, kbuf, vbuf)
-        ops.gemm(out, self.llm2vae.weight, bias=self.llm2vae.bias, out=st["v_all"][: nb * n])
+        lm.run_layers(seq, plan, kbuf, vbuf, final_norm=False)
+        if head:
+            self._velocity_head(st, key)
         return nb
+
+    def _velocity_head(self, st: Dict[str, Any], key: str):
+        """Final norm + llm2vae (bagel.py:832) over the hidden state in the LM's "xa" workspace."""
+        lm = self.language_model.model
+        plan, _, _, nb = st[key]
+        out = lm.final_norm(plan)
+        ops.gemm(out, self.llm2vae.weight, bias=self.llm2vae.bias, out=st["v_all"][: nb * st["n"]])
 
     def _cfg_update(self, st: Dict[str, Any], nb: int, scales: Tuple[float, float], renorm_min: float,
                     renorm_type: str, x_dst: torch.Tensor, dt: float, dt_dev: Optional[torch.Tensor] = None):
@@ -462,8 +471,6 @@ class Bagel:
                          cfg_type: str = "parallel", enable_taylorseer: bool = False) -> "FlowRunner":
         """Plan a whole denoising run (same arguments as generate_image); FlowRunner.step(i) then executes
         velocity evaluation + CFG + Euler update number i as a sync-free kernel sequence."""
-        if enable_taylorseer:
-            raise NotImplementedError("TaylorSeer step caching is out of scope (SURVEY.md §8f #1)")
         if cfg_renorm_type not in ops.RENORM:
             raise NotImplementedError(f"{cfg_renorm_type} is not suppoprted")
         dev = self.device
@@ -498,7 +505,8 @@ class Bagel:
         if (not all(cfg_on)) or nbmax == 1:
             st["main"] = (*self._build_flow_plan(branches[:1], packed_seqlens, st["vae_idx"], st["txt_idx"]), 1)
         return FlowRunner(self, st, dts.tolist(), cfg_on, (cfg_text_scale, cfg_img_scale), cfg_renorm_min,
-                          cfg_renorm_type, nbmax, torch.as_tensor(packed_seqlens).to("cpu", torch.int64))
+                          cfg_renorm_type, nbmax, torch.as_tensor(packed_seqlens).to("cpu", torch.int64),
+                          enable_taylorseer=enable_taylorseer)
 
     @torch.no_grad()
     def generate_image(self, *args, **kwargs):
@@ -681,7 +689,8 @@ class FlowRunner:
     that change (timestep embedding row, dt) live in fixed device buffers, so the launch sequence of a step is
     captured ONCE per branch set as a CUDA graph and replayed for the remaining steps."""
 
-    def __init__(self, model: Bagel, st, dts, cfg_on, scales, renorm_min, renorm_type, nbmax, seqlens):
+    def __init__(self, model: Bagel, st, dts, cfg_on, scales, renorm_min, renorm_type, nbmax, seqlens,
+                 enable_taylorseer: bool = False):
         self.model, self.st, self.dts, self.cfg_on = model, st, dts, cfg_on
         self.scales, self.renorm_min, self.renorm_type, self.nbmax = scales, renorm_min, renorm_type, nbmax
         self.seqlens = seqlens
@@ -693,8 +702,19 @@ class FlowRunner:
         self.use_cuda_graph = bool(getattr(model, "use_cuda_graph", True))
         self._graphs: Dict[str, Any] = {}
         self._eager_done: Dict[str, int] = {}
+        # TaylorSeer (reference bagel.py:680-684): one schedule per branch; factor planes of the last decoder
+        # layer's output for every packed row of every branch, [7 orders, nbmax*n, H] bf16
+        self.taylor = None
+        if enable_taylorseer:
+            from .taylorseer import TaylorSeerSchedule
+            self.taylor = [TaylorSeerSchedule(len(dts) + 1) for _ in range(nbmax)]
+            self.factors = torch.empty((TaylorSeerSchedule.MAX_ORDER + 1, nbmax * st["n"], model.hidden_size),
+                                       dtype=BF16, device=dev)
 
     def _body(self, key: str):
+        if self.taylor is not None:     # layers only; the cache update / extrapolation and the head follow eagerly
+            self.model._velocity(self.st, key, self.t_cur, self.st["x"], head=False)
+            return
         m, st = self.model, self.st
         on = key == "full"
         nb = m._velocity(st, key, self.t_cur, st["x"])
@@ -706,6 +726,38 @@ class FlowRunner:
         key = "full" if (self.cfg_on[i] and self.nbmax > 1) else "main"
         self.t_cur.copy_(self.st["t_emb"][i])
         self.dt_cur.copy_(self.dts_dev[i:i + 1])
+        if self.taylor is not None:
+            return self._step_taylorseer(key)
+        self._launch(key)
+
+    def _step_taylorseer(self, key: str):
+        """One evaluation with the step cache. Branches are extra samples of one packed LM call, so the layers run
+        whenever ANY active branch needs a fully computed step (with the reference's schedules the active branches
+        always agree); branches on an extrapolated step get their rows of the last-layer output replaced."""
+        m, st = self.model, self.st
+        lm = m.language_model.model
+        nb = st[key][3]
+        n, H = st["n"], m.hidden_size
+        scheds = self.taylor[:nb]
+        types = [s.begin_step() for s in scheds]
+        if any(t == "full" for t in types):
+            self._launch(key)                                # embeddings + all decoder layers -> "xa"
+        xa = lm._buf("xa", nb * n, H)
+        for b, s in enumerate(scheds):
+            rows = slice(b * n, (b + 1) * n)
+            if s.type == "full":
+                n_deriv, dist = s.full_update_args()
+                ops.taylor_update(xa[rows], self.factors[:, rows], n_deriv, dist)
+            else:
+                n_f, x = s.taylor_args()
+                ops.taylor_eval(self.factors[:, rows], n_f, x, xa[rows])
+            s.end_step()
+        m._velocity_head(st, key)
+        on = key == "full"
+        m._cfg_update(st, nb, self.scales if on else (1.0, 1.0), self.renorm_min, self.renorm_type, st["x"], 0.0,
+                      self.dt_cur)
+
+    def _launch(self, key: str):
         g = self._graphs.get(key)
         if g is not None:
             g.replay()

@@ -479,6 +479,80 @@ argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int V
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TaylorSeer step cache (reference modeling/cache_utils/taylorseer.py; hooks qwen2_navit.py:773-777, 824-829).
+// Factors are bf16 planes [order][rows][H] of the LAST decoder layer's output (on an extrapolated step each layer's
+// output replaces its input, so only the last layer's extrapolation reaches the result). Both kernels are pure HBM
+// streams over [rows, H] and reproduce torch's bf16 elementwise rounding: every binary op rounds to bf16, python
+// scalars enter as fp32.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTaylorMaxPlanes = 7;   // max_order 6 -> factors 0..6
+
+// derivative_approximation (:12-32): new[0] = feature; new[i+1] = bf16(bf16(new[i] - old[i]) / dist), i < n_deriv.
+// In place: the old factors of an element are read before any plane is rewritten.
+__global__ void __launch_bounds__(256)
+taylor_update_kernel(const __nv_bfloat16* __restrict__ feature, long long ldf, __nv_bfloat16* __restrict__ factors,
+                     long long plane, int n_deriv, float dist, int rows, int vec_per_row) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * vec_per_row) return;
+  const int row = (int)(idx / vec_per_row), c = (int)(idx - (long long)row * vec_per_row);
+  const uint4 f = *reinterpret_cast<const uint4*>(feature + (long long)row * ldf + c * 8);
+  __nv_bfloat16* dst = factors + ((long long)row * vec_per_row + c) * 8;
+  uint4 old[kTaylorMaxPlanes - 1];
+#pragma unroll
+  for (int i = 0; i < kTaylorMaxPlanes - 1; ++i)
+    if (i < n_deriv) old[i] = *reinterpret_cast<const uint4*>(dst + i * plane);
+  uint32_t cur[4] = {f.x, f.y, f.z, f.w};
+  *reinterpret_cast<uint4*>(dst) = f;
+#pragma unroll
+  for (int i = 0; i < kTaylorMaxPlanes - 1; ++i) {
+    if (i < n_deriv) {
+      const uint32_t o[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d0 = bf16_round(bf16_lo(cur[e]) - bf16_lo(o[e]));
+        const float d1 = bf16_round(bf16_hi(cur[e]) - bf16_hi(o[e]));
+        cur[e] = pack_bf16x2(__fdiv_rn(d0, dist), __fdiv_rn(d1, dist));
+      }
+      *reinterpret_cast<uint4*>(dst + (long long)(i + 1) * plane) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
+    }
+  }
+}
+
+struct TaylorCoef {
+  float c[kTaylorMaxPlanes];    // 1 / i!
+  float xp[kTaylorMaxPlanes];   // x^i
+};
+
+// taylor_formula (:34-47): out = sum_i bf16(bf16(c_i * f_i) * x^i), accumulated in bf16 in order i = 0, 1, ...
+__global__ void __launch_bounds__(256)
+taylor_eval_kernel(const __nv_bfloat16* __restrict__ factors, long long plane, int n, const TaylorCoef k,
+                   __nv_bfloat16* __restrict__ out, long long ldo, int rows, int vec_per_row) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * vec_per_row) return;
+  const int row = (int)(idx / vec_per_row), c = (int)(idx - (long long)row * vec_per_row);
+  const __nv_bfloat16* src = factors + ((long long)row * vec_per_row + c) * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < kTaylorMaxPlanes; ++i) {
+    if (i < n) {
+      const uint4 f = *reinterpret_cast<const uint4*>(src + i * plane);
+      const uint32_t u[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float t0 = bf16_round(bf16_round(bf16_lo(u[e]) * k.c[i]) * k.xp[i]);
+        const float t1 = bf16_round(bf16_round(bf16_hi(u[e]) * k.c[i]) * k.xp[i]);
+        acc[2 * e] = (i == 0) ? t0 : bf16_round(acc[2 * e] + t0);
+        acc[2 * e + 1] = (i == 0) ? t1 : bf16_round(acc[2 * e + 1] + t1);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (long long)row * ldo + c * 8) =
+      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                 pack_bf16x2(acc[6], acc[7]));
+}
+
 }  // namespace bagel
 
 using namespace bagel;
@@ -660,6 +734,45 @@ extern "C" int bagel_decode_advance(int* seq_len, long long* pos, const long lon
   if (B > 1024) return set_error(BAGEL_ERR_SHAPE, "bagel_decode_advance: B must be <= 1024");
   decode_advance_kernel<<<1, ((B + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream)>>>(seq_len, pos, tokens, history,
                                                                                           step_dev, B);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_taylor_update_bf16(const void* feature, long long ldf, void* factors, long long plane_stride,
+                                        int n_deriv, int dist, int rows, int H, void* stream) {
+  if (rows <= 0) return 0;
+  if ((H % 8) || (ldf % 8) || (plane_stride % 8) || plane_stride < (long long)rows * H)
+    return set_error(BAGEL_ERR_ALIGN, "bagel_taylor_update_bf16: H, ldf, plane_stride %% 8 and plane_stride >= rows*H required");
+  if (n_deriv < 0 || n_deriv > kTaylorMaxPlanes - 1 || (n_deriv > 0 && dist <= 0))
+    return set_error(BAGEL_ERR_ARG, "bagel_taylor_update_bf16: n_deriv must be in [0, 6] with dist > 0");
+  const long long n = (long long)rows * (H / 8);
+  taylor_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(feature), ldf, static_cast<__nv_bfloat16*>(factors), plane_stride, n_deriv,
+      (float)dist, rows, H / 8);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_taylor_eval_bf16(const void* factors, long long plane_stride, int n_factors, int x, void* out,
+                                      long long ldo, int rows, int H, void* stream) {
+  if (rows <= 0) return 0;
+  if ((H % 8) || (ldo % 8) || (plane_stride % 8) || plane_stride < (long long)rows * H)
+    return set_error(BAGEL_ERR_ALIGN, "bagel_taylor_eval_bf16: H, ldo, plane_stride %% 8 and plane_stride >= rows*H required");
+  if (n_factors < 1 || n_factors > kTaylorMaxPlanes)
+    return set_error(BAGEL_ERR_ARG, "bagel_taylor_eval_bf16: n_factors must be in [1, 7]");
+  TaylorCoef k{};
+  double fact = 1.0, xp = 1.0;
+  for (int i = 0; i < kTaylorMaxPlanes; ++i) {
+    if (i > 0) { fact *= i; xp *= x; }
+    k.c[i] = (float)(1.0 / fact);
+    k.xp[i] = (float)xp;
+  }
+  const long long n = (long long)rows * (H / 8);
+  taylor_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(factors), plane_stride, n_factors, k, static_cast<__nv_bfloat16*>(out), ldo, rows,
+      H / 8);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -325,3 +325,29 @@ def decode_advance(seq_len, pos, tokens, history, step_dev):
     rc = _cabi.lib().bagel_decode_advance(_ptr(seq_len), _ptr(pos), _ptr(tokens), _ptr(history), _ptr(step_dev),
                                           seq_len.numel(), _stream())
     _cabi.check(rc, "bagel_decode_advance")
+
+
+def taylor_update(feature: torch.Tensor, factors: torch.Tensor, n_deriv: int, dist: int, rows: Optional[int] = None):
+    """TaylorSeer derivative_approximation (cache_utils/taylorseer.py:12-32) on factor planes [orders, cap_rows, H]
+    (in place): plane 0 <- feature, plane i+1 <- bf16(bf16(plane_i_new - plane_i_old) / dist) for i < n_deriv."""
+    _req(feature, torch.bfloat16, "feature"); _req(factors, torch.bfloat16, "factors")
+    assert factors.dim() == 3 and factors.stride(2) == 1 and factors.stride(1) == factors.shape[2] and feature.stride(1) == 1
+    M = feature.shape[0] if rows is None else int(rows)
+    H = feature.shape[1]
+    assert factors.shape[2] == H and factors.shape[1] >= M and factors.shape[0] >= n_deriv + 1
+    rc = _cabi.lib().bagel_taylor_update_bf16(_ptr(feature), feature.stride(0), _ptr(factors), factors.stride(0),
+                                              int(n_deriv), int(dist), M, H, _stream())
+    _cabi.check(rc, "bagel_taylor_update_bf16")
+
+
+def taylor_eval(factors: torch.Tensor, n_factors: int, x: int, out: torch.Tensor, rows: Optional[int] = None):
+    """TaylorSeer taylor_formula (cache_utils/taylorseer.py:34-47): out = sum_i bf16(bf16(f_i / i!) * x^i)."""
+    _req(factors, torch.bfloat16, "factors"); _req(out, torch.bfloat16, "out")
+    assert factors.dim() == 3 and factors.stride(2) == 1 and factors.stride(1) == factors.shape[2] and out.stride(1) == 1
+    M = out.shape[0] if rows is None else int(rows)
+    H = out.shape[1]
+    assert factors.shape[2] == H and factors.shape[1] >= M and 1 <= n_factors <= factors.shape[0]
+    rc = _cabi.lib().bagel_taylor_eval_bf16(_ptr(factors), factors.stride(0), int(n_factors), int(x), _ptr(out),
+                                            out.stride(0), M, H, _stream())
+    _cabi.check(rc, "bagel_taylor_eval_bf16")
+    return out

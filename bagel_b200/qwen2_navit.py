@@ -186,10 +186,12 @@ class Qwen2Model:
             ops.copy_rows(pv.reshape(plan.n_ctx, w), vbuf[li], dst_rows=plan.ctx_rows, M=plan.n_ctx)
 
     # ----------------------------------------------------------------------------------------------
-    def run_layers(self, x: torch.Tensor, plan: ForwardPlan, kbuf: torch.Tensor, vbuf: torch.Tensor) -> torch.Tensor:
+    def run_layers(self, x: torch.Tensor, plan: ForwardPlan, kbuf: torch.Tensor, vbuf: torch.Tensor,
+                   final_norm: bool = True) -> torch.Tensor:
         """All decoder layers + final norm on a packed bf16 sequence x [n, H]. kbuf/vbuf: [L, total_kv, Hk*D]
         with the context rows already in place; the new K/V rows are written by the qk-norm/RoPE kernel.
-        Pure kernel launches (CUDA-graph capturable)."""
+        Pure kernel launches (CUDA-graph capturable). final_norm=False returns the last layer's output (the
+        TaylorSeer feature, qwen2_navit.py:824-826) and leaves the norm to `final_norm()`."""
         cfg = self.config
         n, H = plan.n, cfg.hidden_size
         Hq, Hk, D, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
@@ -249,8 +251,17 @@ class Qwen2Model:
                 ops.gemm(ht, und.wgu, epilogue=ops.EPI_SWIGLU, out=actt)
                 ops.gemm(actt, und.wd, resid=xb, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xa)
 
+        if not final_norm:
+            return xa
+        return self.final_norm(plan)
+
+    def final_norm(self, plan: ForwardPlan) -> torch.Tensor:
+        """Final (routed) RMSNorm of the hidden state left in the "xa" workspace (qwen2_navit.py:1075-1084)."""
+        n, H = plan.n, self.config.hidden_size
+        routed = plan.expert is not None
+        xa = self._buf("xa", n, H)
         out = self._buf("out", n, H)
-        ops.rmsnorm(xa, self.norm, self.norm_moe_gen if routed else None, plan.expert, eps, out=out)
+        ops.rmsnorm(xa, self.norm, self.norm_moe_gen if routed else None, plan.expert, self.config.rms_norm_eps, out=out)
         return out
 
     # ----------------------------------------------------------------------------------------------

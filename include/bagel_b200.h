@@ -180,6 +180,18 @@ int bagel_argmax_rows_bf16(const void* logits, long long ld, int B, int V, long 
 int bagel_decode_advance(int* seq_len, long long* pos, const long long* tokens, long long* history, int* step_dev, int B,
                          void* stream);
 
+/* TaylorSeer step cache (reference modeling/cache_utils/taylorseer.py, enabled by generate_image(enable_taylorseer=True),
+ * modeling/bagel/bagel.py:678-684; decoder-layer hooks modeling/bagel/qwen2_navit.py:773-777, 824-829).
+ * factors: bf16 planes [order][rows][H], plane_stride elements apart, of the last decoder layer's output.
+ * update  = derivative_approximation (:12-32) on a fully computed step:
+ *           new[0] = feature; new[i+1] = bf16(bf16(new[i] - old[i]) / dist) for i < n_deriv  (in place).
+ * eval    = taylor_formula (:34-47) on a skipped step: out = sum_{i<n_factors} bf16(bf16(f_i / i!) * x^i), bf16 adds,
+ *           x = steps since the last fully computed one. Bit-exact w.r.t. torch's bf16 elementwise semantics. */
+int bagel_taylor_update_bf16(const void* feature, long long ldf, void* factors, long long plane_stride, int n_deriv,
+                             int dist, int rows, int H, void* stream);
+int bagel_taylor_eval_bf16(const void* factors, long long plane_stride, int n_factors, int x, void* out, long long ldo,
+                           int rows, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

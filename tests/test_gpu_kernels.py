@@ -373,3 +373,43 @@ def test_argmax_rows_first_max_index(B, V):
     lf = logits.float()
     first = (lf == lf.amax(1, keepdim=True)).float().argmax(1)   # first index of the maximum
     assert torch.equal(tok, first) and torch.equal(tok32.long(), first)
+
+
+def test_taylorseer_kernels_bit_exact_vs_torch_semantics():
+    """ops.taylor_update / ops.taylor_eval against the oracle's restatement of cache_utils/taylorseer.py run on the
+    same bf16 tensors on the host: elementwise bf16 arithmetic, so the kernels must agree BIT FOR BIT through a whole
+    schedule (full steps 0-4, 7, 10, 13, 16, 19, 22 -> all 6 orders; extrapolated steps in between)."""
+    from bagel_b200.taylorseer import TaylorSeerSchedule
+    g = torch.Generator(device=DEV).manual_seed(5)
+    rows, cap, H = 37, 50, 256
+    factors = torch.zeros(7, cap, H, device=DEV, dtype=torch.bfloat16)
+    sched = TaylorSeerSchedule(26)
+    ora = om.TaylorSeerState(1, 26)
+    base = torch.randn(rows, H, device=DEV, generator=g)
+    drift = torch.randn(rows, H, device=DEV, generator=g)
+    out = torch.empty(rows, H, device=DEV, dtype=torch.bfloat16)
+    n_full = n_taylor = 0
+    for step in range(25):
+        ora.cal_type()
+        assert sched.begin_step() == ora.type
+        if ora.type == "full":
+            feat = (base + 0.05 * step * drift + 0.01 * torch.randn(rows, H, device=DEV, generator=g)).to(torch.bfloat16)
+            if ora.step == 0:
+                ora.factors[0] = {}
+            ora.derivative_approximation(0, feat.cpu())
+            n_deriv, dist = sched.full_update_args()
+            ops.taylor_update(feat, factors[:, 5:5 + rows], n_deriv, dist)      # a row window of the planes
+            assert sched.n_factors == len(ora.factors[0])
+            for i, f in ora.factors[0].items():
+                assert torch.equal(factors[i, 5:5 + rows].cpu(), f), f"step {step} factor {i}"
+            n_full += 1
+        else:
+            ref = ora.taylor_formula(0)
+            n_f, x = sched.taylor_args()
+            ops.taylor_eval(factors[:, 5:5 + rows], n_f, x, out)
+            assert torch.equal(out.cpu(), ref), f"step {step} (x={x}, {n_f} factors)"
+            n_taylor += 1
+        ora.step += 1
+        sched.end_step()
+    assert n_full == 11 and n_taylor == 14 and sched.n_factors == 7
+    assert bool((factors[:, :5] == 0).all()) and bool((factors[:, 5 + rows:] == 0).all())

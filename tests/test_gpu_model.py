@@ -105,7 +105,10 @@ def _contexts(model, cfg):
 
 
 VARIANTS = [("nocfg", 1.0, 1.0, "global"), ("global", 4.0, 1.0, "global"), ("channel", 4.0, 1.0, "channel"),
-            ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel")]
+            ("global_img", 4.0, 1.5, "global"), ("text_channel_img", 4.0, 1.5, "text_channel"),
+            # enable_taylorseer=True: 13 evaluations, 7 computed + 6 extrapolated (Taylor orders up to 3)
+            ("taylor_nocfg", 1.0, 1.0, "global"), ("taylor_global_img", 4.0, 1.5, "global"),
+            ("taylor_text_channel", 4.0, 1.0, "text_channel")]
 
 
 @pytest.mark.parametrize("name,sT,sI,rt", VARIANTS)
@@ -124,8 +127,9 @@ def test_generate_image_tiny(g_flow, name, sT, sI, rt):
         assert torch.equal(gi[k], g_flow["latent." + k]), k
     ct = model.prepare_vae_latent_cfg(kv_t, rp_t, helpers.IMAGE_SIZES)
     ci = model.prepare_vae_latent_cfg(kv_i, rp_i, helpers.IMAGE_SIZES)
-    kw = dict(num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type=rt, cfg_interval=[0.4, 1.0],
-              cfg_text_scale=sT, cfg_img_scale=sI)
+    taylor = name.startswith("taylor_")
+    kw = dict(num_timesteps=14 if taylor else 4, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type=rt,
+              cfg_interval=[0.4, 1.0], cfg_text_scale=sT, cfg_img_scale=sI, enable_taylorseer=taylor)
     lat = model.generate_image(
         past_key_values=c_main, **gi, **kw,
         cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
@@ -137,7 +141,8 @@ def test_generate_image_tiny(g_flow, name, sT, sI, rt):
     torch.cuda.synchronize()
     assert [tuple(x.shape) for x in lat] == [(16, 64), (24, 64)] and lat[0].dtype == torch.float32
     got = torch.cat(lat, 0).cpu()
-    ref = g_flow[f"gen.{name}.latents"]
+    ref = (load_file(os.path.join(os.path.dirname(__file__), "golden", "flow_taylor_tiny.safetensors")) if taylor
+           else g_flow)[f"gen.{name}.latents"]
 
     # exact answer on the host: fp32 everywhere, same bf16-valued weights and the same init noise
     sd32 = _f32(helpers.flow_state_dict(cfg))
@@ -158,6 +163,8 @@ def test_generate_image_tiny(g_flow, name, sT, sI, rt):
     truth = torch.cat(truth, 0)
     # CFG scale 4 amplifies branch differences 4x (and the image CFG again 1.5x)
     amp = 1.0 if sT <= 1 else (4.0 if sI <= 1 else 6.0)
+    if taylor:   # 13 evaluations instead of 3, and finite differences of bf16 features extrapolated 1-2 steps ahead
+        amp *= 3.0
     _check(f"latents[{name}]", got, ref, truth, max_ulps_of_scale=2.0 * amp)
 
 
