@@ -7,7 +7,8 @@
 // walk the keys serially. Here instead:
 //   * grid = (split, Hk, batch): the keys of one (sample, kv head) are split over the CTAs of a thread-block
 //     CLUSTER; each CTA handles all G = Hq/Hk query heads that share the kv head, so K and V are read exactly once;
-//   * scores: one key row per lane (no cross-lane reduction), q broadcast from shared memory in fp32;
+//   * scores: warp-level m16n8k16 MMAs whose fragments are loaded straight from global memory (the contraction
+//     index is permuted identically for q and k, so every lane reads whole 16-byte chunks; no shared-memory staging);
 //   * P*V: one 4-wide slice of head_dim per lane, V rows read coalesced (256 B per row per warp);
 //   * flash-decoding merge: warps -> CTA through shared memory, CTAs -> rank 0 of the cluster through distributed
 //     shared memory, fixed order (deterministic), no workspace, one launch.
@@ -49,128 +50,163 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank)
   return v;
 }
 
+// m16n8k16 bf16 x bf16 -> fp32 (legacy warp-level tensor-core path; the 7-8 query heads of a GQA group are the M rows)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kBlk = 16;   // keys per warp iteration (two 8-key MMA column tiles)
+
+// Scores on tensor cores WITHOUT staging K in shared memory: the contraction index of q.k may be permuted freely as
+// long as q and k use the same permutation, so lane (g = lane/4, j = lane%4) loads the 16-byte chunks j, j+4, j+8,
+// j+12 of "its" key row (coalesced: 4 lanes x 16 B per key, 8 keys per instruction) and feeds each chunk to two
+// m16n8k16 MMAs as the B fragment; the A fragments are the same chunks of the q rows (row g = query head g of the
+// group, rows 8-15 zero). P*V stays on the FMA pipe: lane <-> 4 channels, probabilities broadcast from shared memory.
 template <int G>
 __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodeParams p) {
-  __shared__ __align__(16) float sq[G][kD];            // q * softmax_scale * log2(e)
-  __shared__ __align__(16) float sp[kWarps][G][32];    // probabilities of the warp's current 32-key block
+  __shared__ __align__(16) float sp[kWarps][G][kBlk];  // probabilities of the warp's current key block
+  __shared__ float s_corr[kWarps][8];                  // per-head rescale of the running output for this block
   __shared__ __align__(16) float s_acc[kWarps][G][kD];
   __shared__ float s_m[kWarps][G], s_l[kWarps][G];
   __shared__ __align__(16) float part_acc[G][kD];      // this CTA's (un-normalised) partial, read by cluster rank 0
   __shared__ float part_m[G], part_l[G];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  const int g = lane >> 2, j = lane & 3;
   const int rank = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int q_row = p.cu_q[b];
   const bool active = (p.cu_q[b + 1] - q_row) > 0;
   const int k_begin = p.cu_k[b];
   int len = p.seqused_k ? p.seqused_k[b] : (p.cu_k[b + 1] - k_begin);
   if (!active || len < 0) len = 0;
-  const int chunk = (((len + p.split - 1) / p.split) + 31) & ~31;
+  const int chunk = (((len + p.split - 1) / p.split) + kBlk - 1) & ~(kBlk - 1);
   const int r0 = min(rank * chunk, len), r1 = min(r0 + chunk, len);
 
-  if (active) {
+  // A fragments: q row of head g (zero rows for g >= G), chunk (j + 4t) -> k-steps 2t, 2t+1
+  uint4 qq[4];
 #pragma unroll
-    for (int h = 0; h < G; ++h)
-      sq[h][t] = __bfloat162float(p.q[(long long)q_row * p.ld_q + (hk * G + h) * kD + t]) * p.scale_log2;
+  for (int tt = 0; tt < 4; ++tt) qq[tt] = make_uint4(0u, 0u, 0u, 0u);
+  if (active && g < G) {
+    const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)q_row * p.ld_q + (hk * G + g) * kD);
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) qq[tt] = __ldg(qp + j + 4 * tt);
   }
-  __syncthreads();
 
-  float m[G], l[G], acc[G][4];
+  float m_run = -INFINITY, l_run = 0.f;   // state of head g (replicated over the 4 lanes j; l is a per-lane partial)
+  float acc[G][4];
 #pragma unroll
-  for (int h = 0; h < G; ++h) {
-    m[h] = -INFINITY;
-    l[h] = 0.f;
-    acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
-  }
+  for (int h = 0; h < G; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
 
   const __nv_bfloat16* kbase = p.k + (long long)k_begin * p.ld_k + hk * kD;
   const __nv_bfloat16* vbase = p.v + (long long)k_begin * p.ld_v + hk * kD;
 
-  for (int blk = r0 + warp * 32; blk < r1; blk += kWarps * 32) {
-    const int row = blk + lane;
-    const bool valid = row < r1;
-    // ---- scores: lane <-> key row ----
-    const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)(valid ? row : r1 - 1) * p.ld_k);
-    uint4 kk[16];
+  auto load_k = [&](int blk, uint4 (&kk)[2][4]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) kk[i] = __ldg(kp + i);
-    float s[G], s2[G];
+    for (int nt = 0; nt < 2; ++nt) {
+      const int key = min(blk + nt * 8 + g, r1 - 1);   // keys past the end are masked below
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)key * p.ld_k);
 #pragma unroll
-    for (int h = 0; h < G; ++h) s[h] = s2[h] = 0.f;
+      for (int tt = 0; tt < 4; ++tt) kk[nt][tt] = __ldg(kp + j + 4 * tt);
+    }
+  };
+
+  int blk = r0 + warp * kBlk;
+  uint4 kk[2][4];
+  if (blk < r1) load_k(blk, kk);
+  for (; blk < r1; blk += kWarps * kBlk) {
+    // ---- S = q k^T: 2 key tiles x 8 k-steps ----
+    float sc[2][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {   // 8 channels per step, unpacked once and used by all G heads
-      const float k0 = bf16_lo(kk[i].x), k1 = bf16_hi(kk[i].x), k2 = bf16_lo(kk[i].y), k3 = bf16_hi(kk[i].y);
-      const float k4 = bf16_lo(kk[i].z), k5 = bf16_hi(kk[i].z), k6 = bf16_lo(kk[i].w), k7 = bf16_hi(kk[i].w);
+    for (int nt = 0; nt < 2; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
 #pragma unroll
-      for (int h = 0; h < G; ++h) {
-        const float4 qa = *reinterpret_cast<const float4*>(&sq[h][i * 8]);
-        const float4 qb = *reinterpret_cast<const float4*>(&sq[h][i * 8 + 4]);
-        s[h] = fmaf(k0, qa.x, s[h]);
-        s2[h] = fmaf(k1, qa.y, s2[h]);
-        s[h] = fmaf(k2, qa.z, s[h]);
-        s2[h] = fmaf(k3, qa.w, s2[h]);
-        s[h] = fmaf(k4, qb.x, s[h]);
-        s2[h] = fmaf(k5, qb.y, s2[h]);
-        s[h] = fmaf(k6, qb.z, s[h]);
-        s2[h] = fmaf(k7, qb.w, s2[h]);
+      for (int tt = 0; tt < 4; ++tt) {
+        mma_bf16_16816(sc[nt], qq[tt].x, 0u, qq[tt].y, 0u, kk[nt][tt].x, kk[nt][tt].y);
+        mma_bf16_16816(sc[nt], qq[tt].z, 0u, qq[tt].w, 0u, kk[nt][tt].z, kk[nt][tt].w);
       }
     }
+    // prefetch: V rows of this block (first half) and K of the warp's next block
+    const int nrows = min(kBlk, r1 - blk);
+    uint2 vv[8];
 #pragma unroll
-    for (int h = 0; h < G; ++h) s[h] = valid ? s[h] + s2[h] : -INFINITY;
-    // ---- online softmax (block max over the warp; running state replicated in every lane) ----
+    for (int i = 0; i < 8; ++i)
+      vv[i] = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)min(blk + i, r1 - 1) * p.ld_v + lane * 4));
+    const int nblk = blk + kWarps * kBlk;
+    if (nblk < r1) load_k(nblk, kk);
+
+    // ---- online softmax for head g over this block's 16 keys (4 per lane, 4 lanes per head) ----
+    float sv[4];
 #pragma unroll
-    for (int h = 0; h < G; ++h) {
-      float mb = s[h];
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-      const float m_new = fmaxf(m[h], mb);                       // finite: the block has at least one valid key
-      const float corr = (m[h] == -INFINITY) ? 0.f : ex2f(m[h] - m_new);
-      const float pr = valid ? ex2f(s[h] - m_new) : 0.f;
-      l[h] = l[h] * corr + pr;
-      m[h] = m_new;
-      sp[warp][h][lane] = pr;
-      acc[h][0] *= corr; acc[h][1] *= corr; acc[h][2] *= corr; acc[h][3] *= corr;
+      for (int e = 0; e < 2; ++e)
+        sv[nt * 2 + e] = (blk + nt * 8 + 2 * j + e < r1) ? sc[nt][e] * p.scale_log2 : -INFINITY;
+    float mb = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    const float m_new = fmaxf(m_run, mb);   // finite: the block holds at least one valid key
+    const float corr = (m_run == -INFINITY) ? 0.f : ex2f(m_run - m_new);
+    float pr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = ex2f(sv[i] - m_new);   // ex2(-inf) = 0 for masked keys
+    l_run = l_run * corr + (pr[0] + pr[1]) + (pr[2] + pr[3]);
+    m_run = m_new;
+    if (g < G) {
+      *reinterpret_cast<float2*>(&sp[warp][g][2 * j]) = make_float2(pr[0], pr[1]);
+      *reinterpret_cast<float2*>(&sp[warp][g][8 + 2 * j]) = make_float2(pr[2], pr[3]);
+      if (j == 0) s_corr[warp][g] = corr;
     }
     __syncwarp();
-    // ---- P*V: lane <-> 4 consecutive channels; 32 key rows, 8 in flight ----
-    const int nrows = min(32, r1 - blk);
-#pragma unroll 1
-    for (int r8 = 0; r8 < nrows; r8 += 8) {
-      uint2 vv[8];
+    // ---- O = O * corr + P V: lane <-> 4 consecutive channels ----
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int rr = min(blk + r8 + j, r1 - 1);                // rows past the end carry p = 0
-        vv[j] = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)rr * p.ld_v + lane * 4));
+    for (int h = 0; h < G; ++h) {
+      const float c = s_corr[warp][h];
+      acc[h][0] *= c; acc[h][1] *= c; acc[h][2] *= c; acc[h][3] *= c;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1) {
+        if (nrows <= 8) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          vv[i] = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)min(blk + 8 + i, r1 - 1) * p.ld_v + lane * 4));
+      }
+      float v0[8], v1[8], v2[8], v3[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v0[i] = bf16_lo(vv[i].x); v1[i] = bf16_hi(vv[i].x); v2[i] = bf16_lo(vv[i].y); v3[i] = bf16_hi(vv[i].y);
       }
 #pragma unroll
       for (int h = 0; h < G; ++h) {
-        const float4 pa = *reinterpret_cast<const float4*>(&sp[warp][h][r8]);
-        const float4 pb = *reinterpret_cast<const float4*>(&sp[warp][h][r8 + 4]);
+        const float4 pa = *reinterpret_cast<const float4*>(&sp[warp][h][half * 8]);
+        const float4 pb = *reinterpret_cast<const float4*>(&sp[warp][h][half * 8 + 4]);
         const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[h][0] = fmaf(pj[j], bf16_lo(vv[j].x), acc[h][0]);
-          acc[h][1] = fmaf(pj[j], bf16_hi(vv[j].x), acc[h][1]);
-          acc[h][2] = fmaf(pj[j], bf16_lo(vv[j].y), acc[h][2]);
-          acc[h][3] = fmaf(pj[j], bf16_hi(vv[j].y), acc[h][3]);
+        for (int i = 0; i < 8; ++i) {
+          acc[h][0] = fmaf(pj[i], v0[i], acc[h][0]);
+          acc[h][1] = fmaf(pj[i], v1[i], acc[h][1]);
+          acc[h][2] = fmaf(pj[i], v2[i], acc[h][2]);
+          acc[h][3] = fmaf(pj[i], v3[i], acc[h][3]);
         }
       }
     }
-    __syncwarp();   // sp[warp] is rewritten by the next block
+    __syncwarp();   // sp / s_corr of this warp are rewritten by the next block
   }
 
   // ---- merge: lanes -> warp -> CTA ----
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    float ls = l[h];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-    *reinterpret_cast<float4*>(&s_acc[warp][h][lane * 4]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
-    if (lane == 0) {
-      s_m[warp][h] = m[h];
-      s_l[warp][h] = ls;
-    }
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (g < G && j == 0) {
+    s_m[warp][g] = m_run;
+    s_l[warp][g] = l_run;
   }
+#pragma unroll
+  for (int h = 0; h < G; ++h)
+    *reinterpret_cast<float4*>(&s_acc[warp][h][lane * 4]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
   __syncthreads();
 #pragma unroll
   for (int h = 0; h < G; ++h) {
@@ -254,7 +290,7 @@ int attn_decode(const void* q, const void* k, const void* v, void* out, const in
   p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ld_out = ld_out;
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.seqused_k = seqused_k;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  // keys per CTA ~128 (one 32-key block per warp), cluster size <= 8; unknown max length -> 8
+  // keys per CTA ~128 (two 16-key blocks per warp), cluster size <= 8; unknown max length -> 8
   int split = (max_seqlen_k > 0) ? (max_seqlen_k + 127) / 128 : 8;
   if (split > 8) split = 8;
   if (split < 1) split = 1;
