@@ -7,8 +7,9 @@
 // walk the keys serially. Here instead:
 //   * grid = (split, Hk, batch): the keys of one (sample, kv head) are split over the CTAs of a thread-block
 //     CLUSTER; each CTA handles all G = Hq/Hk query heads that share the kv head, so K and V are read exactly once;
-//   * scores: warp-level m16n8k16 MMAs whose fragments are loaded straight from global memory (the contraction
-//     index is permuted identically for q and k, so every lane reads whole 16-byte chunks; no shared-memory staging);
+//   * K/V stream through per-warp cp.async rings (3 stages x 16 keys), ~190 KB in flight per SM;
+//   * scores: warp-level m16n8k16 MMAs; the contraction index is permuted identically for q and k, so every lane
+//     feeds whole 16-byte chunks as fragments (no transposes, conflict-free swizzled reads);
 //   * P*V: one 4-wide slice of head_dim per lane, V rows read coalesced (256 B per row per warp);
 //   * flash-decoding merge: warps -> CTA through shared memory, CTAs -> rank 0 of the cluster through distributed
 //     shared memory, fixed order (deterministic), no workspace, one launch.
@@ -59,21 +60,36 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int kBlk = 16;   // keys per warp iteration (two 8-key MMA column tiles)
+constexpr int kBlk = 16;        // keys per warp iteration (two 8-key MMA column tiles)
+constexpr int kStages = 3;      // per-warp cp.async ring depth
+constexpr int kTileBytes = kBlk * kD * 2;            // 4 KB: one K (or V) tile of 16 keys
+constexpr int kStageBytes = 2 * kTileBytes;          // K tile then V tile
+constexpr int kRingBytes = kWarps * kStages * kStageBytes;   // 96 KB -> two CTAs per SM
 
-// Scores on tensor cores WITHOUT staging K in shared memory: the contraction index of q.k may be permuted freely as
-// long as q and k use the same permutation, so lane (g = lane/4, j = lane%4) loads the 16-byte chunks j, j+4, j+8,
-// j+12 of "its" key row (coalesced: 4 lanes x 16 B per key, 8 keys per instruction) and feeds each chunk to two
-// m16n8k16 MMAs as the B fragment; the A fragments are the same chunks of the q rows (row g = query head g of the
-// group, rows 8-15 zero). P*V stays on the FMA pipe: lane <-> 4 channels, probabilities broadcast from shared memory.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// K/V stream: every warp owns a 3-stage cp.async ring (16 keys x (256 B K + 256 B V) per stage), so ~24 KB per warp
+// (~190 KB per SM) are in flight independent of the register file — this kernel is a latency-bound HBM stream.
+// Scores on tensor cores: the contraction index of q.k may be permuted freely as long as q and k use the same
+// permutation, so lane (g = lane/4, j = lane%4) takes the 16-byte chunks j, j+4, j+8, j+12 of "its" key row as the
+// B fragments of two m16n8k16 MMAs each; the A fragments are the same chunks of the q rows (row g = query head g of
+// the group, rows 8-15 zero). K chunks are stored XOR-swizzled (bit 2 of the chunk index flipped on odd keys) so the
+// fragment reads are bank-conflict free. P*V stays on the FMA pipe: lane <-> 4 channels, probabilities broadcast from
+// shared memory.
 template <int G>
-__global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodeParams p) {
+  extern __shared__ __align__(128) uint8_t ring[];     // [kWarps][kStages][K tile | V tile]; reused for the merge
   __shared__ __align__(16) float sp[kWarps][G][kBlk];  // probabilities of the warp's current key block
   __shared__ float s_corr[kWarps][8];                  // per-head rescale of the running output for this block
-  __shared__ __align__(16) float s_acc[kWarps][G][kD];
   __shared__ float s_m[kWarps][G], s_l[kWarps][G];
   __shared__ __align__(16) float part_acc[G][kD];      // this CTA's (un-normalised) partial, read by cluster rank 0
   __shared__ float part_m[G], part_l[G];
+  float (*s_acc)[G][kD] = reinterpret_cast<float (*)[G][kD]>(ring);   // [kWarps][G][kD], valid after the key loop
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
   const int g = lane >> 2, j = lane & 3;
@@ -85,6 +101,29 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
   if (!active || len < 0) len = 0;
   const int chunk = (((len + p.split - 1) / p.split) + kBlk - 1) & ~(kBlk - 1);
   const int r0 = min(rank * chunk, len), r1 = min(r0 + chunk, len);
+
+  const __nv_bfloat16* kbase = p.k + (long long)k_begin * p.ld_k + hk * kD;
+  const __nv_bfloat16* vbase = p.v + (long long)k_begin * p.ld_v + hk * kD;
+  const uint32_t wring = smem_u32(ring) + warp * (kStages * kStageBytes);
+
+  // block i of this warp starts at key r0 + (warp + i*kWarps)*kBlk; rows past r1 are clamped (and masked later)
+  auto issue = [&](int i) {
+    const int blk = r0 + (warp + i * kWarps) * kBlk;
+    if (blk < r1) {
+      const uint32_t st = wring + (i % kStages) * kStageBytes;
+      const int c = lane & 15;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int kl = (lane >> 4) + 2 * r;                       // key within the block
+        const long long key = min(blk + kl, r1 - 1);
+        cp_async16(st + kl * 256 + ((c ^ ((kl & 1) << 2)) << 4), kbase + key * p.ld_k + c * 8);
+        cp_async16(st + kTileBytes + kl * 256 + (c << 4), vbase + key * p.ld_v + c * 8);
+      }
+    }
+    cp_async_commit();   // always commit: group counting stays uniform
+  };
+#pragma unroll
+  for (int i = 0; i < kStages - 1; ++i) issue(i);
 
   // A fragments: q row of head g (zero rows for g >= G), chunk (j + 4t) -> k-steps 2t, 2t+1
   uint4 qq[4];
@@ -101,42 +140,29 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
 #pragma unroll
   for (int h = 0; h < G; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
 
-  const __nv_bfloat16* kbase = p.k + (long long)k_begin * p.ld_k + hk * kD;
-  const __nv_bfloat16* vbase = p.v + (long long)k_begin * p.ld_v + hk * kD;
+  for (int i = 0;; ++i) {
+    const int blk = r0 + (warp + i * kWarps) * kBlk;
+    if (blk >= r1) break;
+    issue(i + kStages - 1);
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    const uint32_t st = wring + (i % kStages) * kStageBytes;
 
-  auto load_k = [&](int blk, uint4 (&kk)[2][4]) {
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int key = min(blk + nt * 8 + g, r1 - 1);   // keys past the end are masked below
-      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)key * p.ld_k);
-#pragma unroll
-      for (int tt = 0; tt < 4; ++tt) kk[nt][tt] = __ldg(kp + j + 4 * tt);
-    }
-  };
-
-  int blk = r0 + warp * kBlk;
-  uint4 kk[2][4];
-  if (blk < r1) load_k(blk, kk);
-  for (; blk < r1; blk += kWarps * kBlk) {
     // ---- S = q k^T: 2 key tiles x 8 k-steps ----
     float sc[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      const int kl = nt * 8 + g;
 #pragma unroll
       for (int tt = 0; tt < 4; ++tt) {
-        mma_bf16_16816(sc[nt], qq[tt].x, 0u, qq[tt].y, 0u, kk[nt][tt].x, kk[nt][tt].y);
-        mma_bf16_16816(sc[nt], qq[tt].z, 0u, qq[tt].w, 0u, kk[nt][tt].z, kk[nt][tt].w);
+        uint4 kk;
+        const uint32_t a = st + kl * 256 + (((j + 4 * tt) ^ ((kl & 1) << 2)) << 4);
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kk.x), "=r"(kk.y), "=r"(kk.z), "=r"(kk.w) : "r"(a));
+        mma_bf16_16816(sc[nt], qq[tt].x, 0u, qq[tt].y, 0u, kk.x, kk.y);
+        mma_bf16_16816(sc[nt], qq[tt].z, 0u, qq[tt].w, 0u, kk.z, kk.w);
       }
     }
-    // prefetch: V rows of this block (first half) and K of the warp's next block
-    const int nrows = min(kBlk, r1 - blk);
-    uint2 vv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      vv[i] = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)min(blk + i, r1 - 1) * p.ld_v + lane * 4));
-    const int nblk = blk + kWarps * kBlk;
-    if (nblk < r1) load_k(nblk, kk);
 
     // ---- online softmax for head g over this block's 16 keys (4 per lane, 4 lanes per head) ----
     float sv[4];
@@ -152,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
     const float corr = (m_run == -INFINITY) ? 0.f : ex2f(m_run - m_new);
     float pr[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pr[i] = ex2f(sv[i] - m_new);   // ex2(-inf) = 0 for masked keys
+    for (int e = 0; e < 4; ++e) pr[e] = ex2f(sv[e] - m_new);   // ex2(-inf) = 0 for masked keys
     l_run = l_run * corr + (pr[0] + pr[1]) + (pr[2] + pr[3]);
     m_run = m_new;
     if (g < G) {
@@ -167,18 +193,16 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
       const float c = s_corr[warp][h];
       acc[h][0] *= c; acc[h][1] *= c; acc[h][2] *= c; acc[h][3] *= c;
     }
+    const int nrows = min(kBlk, r1 - blk);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      if (half == 1) {
-        if (nrows <= 8) break;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          vv[i] = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)min(blk + 8 + i, r1 - 1) * p.ld_v + lane * 4));
-      }
+      if (half * 8 >= nrows) break;
       float v0[8], v1[8], v2[8], v3[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v0[i] = bf16_lo(vv[i].x); v1[i] = bf16_hi(vv[i].x); v2[i] = bf16_lo(vv[i].y); v3[i] = bf16_hi(vv[i].y);
+      for (int r = 0; r < 8; ++r) {
+        uint32_t x, y;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(st + kTileBytes + (half * 8 + r) * 256 + lane * 8));
+        v0[r] = bf16_lo(x); v1[r] = bf16_hi(x); v2[r] = bf16_lo(y); v3[r] = bf16_hi(y);
       }
 #pragma unroll
       for (int h = 0; h < G; ++h) {
@@ -186,16 +210,18 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
         const float4 pb = *reinterpret_cast<const float4*>(&sp[warp][h][half * 8 + 4]);
         const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[h][0] = fmaf(pj[i], v0[i], acc[h][0]);
-          acc[h][1] = fmaf(pj[i], v1[i], acc[h][1]);
-          acc[h][2] = fmaf(pj[i], v2[i], acc[h][2]);
-          acc[h][3] = fmaf(pj[i], v3[i], acc[h][3]);
+        for (int r = 0; r < 8; ++r) {
+          acc[h][0] = fmaf(pj[r], v0[r], acc[h][0]);
+          acc[h][1] = fmaf(pj[r], v1[r], acc[h][1]);
+          acc[h][2] = fmaf(pj[r], v2[r], acc[h][2]);
+          acc[h][3] = fmaf(pj[r], v3[r], acc[h][3]);
         }
       }
     }
-    __syncwarp();   // sp / s_corr of this warp are rewritten by the next block
+    __syncwarp();   // sp / s_corr and this ring stage are rewritten by the next iterations
   }
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with its ring: the merge buffers alias it
 
   // ---- merge: lanes -> warp -> CTA ----
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
@@ -252,10 +278,16 @@ __global__ void __launch_bounds__(kThreads, 3) attn_decode_kernel(const DecodePa
 
 template <int G>
 int launch(const DecodeParams& p, int Hk, int B, cudaStream_t stream) {
+  auto kern = attn_decode_kernel<G>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+    attr_done = true;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)p.split, (unsigned)Hk, (unsigned)B);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = kRingBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -264,7 +296,7 @@ int launch(const DecodeParams& p, int Hk, int B, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BAGEL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_decode_kernel<G>, p));
+  BAGEL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -290,13 +322,15 @@ int attn_decode(const void* q, const void* k, const void* v, void* out, const in
   p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ld_out = ld_out;
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.seqused_k = seqused_k;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  // keys per CTA ~128 (two 16-key blocks per warp), cluster size <= 8; unknown max length -> 8
-  int split = (max_seqlen_k > 0) ? (max_seqlen_k + 127) / 128 : 8;
-  if (split > 8) split = 8;
-  if (split < 1) split = 1;
-  // small batches: more CTAs per (sample, kv head) do not help below one block per warp; large batches: keep the
-  // grid within a few waves
-  while (split > 1 && (long long)batch * Hk * split > 16LL * sm_count()) split >>= 1;
+  // Two CTAs (8 warps, 8 cp.async rings) fit an SM: aim for one wave of ~2 CTAs per SM, at least 64 keys per CTA,
+  // cluster size <= 8 (power of two: odd cluster sizes place badly, see gemm_skinny.cu).
+  static const int env_split = [] { const char* e = getenv("BAGEL_DECODE_SPLIT"); return e ? atoi(e) : 0; }();
+  const long long pairs = (long long)batch * Hk;
+  int split = 1;
+  while (split < 8 && pairs * split * 2 <= 2LL * sm_count()) split *= 2;
+  if (max_seqlen_k > 0)
+    while (split > 1 && (max_seqlen_k + split - 1) / split < 64) split >>= 1;
+  if (env_split > 0) split = env_split;
   p.split = split;
   switch (Hq / Hk) {
     case 1: return launch<1>(p, Hk, batch, stream);

@@ -276,11 +276,18 @@ int gemm_skinny(const void* A, long long lda, const void* W, long long ldw, void
 
   // split-K (cluster size): fill the GPU when there are fewer W slabs than SMs
   static const int env_split = [] { const char* e = getenv("BAGEL_SKINNY_SPLIT"); return e ? atoi(e) : 0; }();
+  static const int env_stages = [] { const char* e = getenv("BAGEL_SKINNY_STAGES"); return e ? atoi(e) : 0; }();
+  // Measured on B200 at B=32 (profiles/r01_skinny_gemm_split_stage_sweep.txt): what matters is (a) >= ~12 K blocks
+  // per CTA, (b) about 1.5 CTAs per SM in total and (c) SMALL shared memory per CTA — a cluster whose CTAs each need a
+  // whole SM (deep ring) often cannot be placed in one GPC and the grid runs in two waves (61 vs 34 us on down_proj).
   int split = 1;
   if (nw == 1) {
     if (env_split > 0) split = env_split;
     else {
-      while (split < 8 && tiles * split * 2 <= sms + sms / 4) split *= 2;   // 28 slabs -> 4, 36 -> 4, 112+ -> 1
+      split = (sms * 8 / 5) / tiles;          // 28 slabs -> 8, 36 -> 6, 1188 -> 0
+      if (split > p.num_k / 12) split = p.num_k / 12;   // K=3584 -> 4, K=18944 -> 24
+      if (split > 8) split = 8;
+      if (split < 1) split = 1;
     }
     if (split > p.num_k) split = p.num_k;
     if (split > 16) split = 16;
@@ -289,8 +296,9 @@ int gemm_skinny(const void* A, long long lda, const void* W, long long ldw, void
 
   const int stage_bytes = nw * 128 * kBK * 2 + p.MT * kBK * 2;
   const long long ctas = (long long)tiles * split;
-  const int budget = (ctas <= sms) ? 196 * 1024 : 104 * 1024;   // one CTA per SM: deep ring; else two CTAs per SM
+  const int budget = (split > 1) ? 4 * stage_bytes : ((ctas <= sms) ? 148 * 1024 : 108 * 1024);
   int stages = budget / stage_bytes;
+  if (env_stages > 0) stages = env_stages;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   const int per_cta_k = (p.num_k + split - 1) / split;
