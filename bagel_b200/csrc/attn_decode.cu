@@ -10,7 +10,7 @@
 //   * K/V stream through per-warp cp.async rings (3 stages x 16 keys), ~190 KB in flight per SM;
 //   * scores: warp-level m16n8k16 MMAs; the contraction index is permuted identically for q and k, so every lane
 //     feeds whole 16-byte chunks as fragments (no transposes, conflict-free swizzled reads);
-//   * P*V: one 4-wide slice of head_dim per lane, V rows read coalesced (256 B per row per warp);
+//   * P*V on the same tensor-core path (P re-packed from the score accumulators, V fragments by ldmatrix.trans);
 //   * flash-decoding merge: warps -> CTA through shared memory, CTAs -> rank 0 of the cluster through distributed
 //     shared memory, fixed order (deterministic), no workspace, one launch.
 #include "common.cuh"
@@ -73,19 +73,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
 // K/V stream: every warp owns a 3-stage cp.async ring (16 keys x (256 B K + 256 B V) per stage), so ~24 KB per warp
 // (~190 KB per SM) are in flight independent of the register file — this kernel is a latency-bound HBM stream.
-// Scores on tensor cores: the contraction index of q.k may be permuted freely as long as q and k use the same
-// permutation, so lane (g = lane/4, j = lane%4) takes the 16-byte chunks j, j+4, j+8, j+12 of "its" key row as the
-// B fragments of two m16n8k16 MMAs each; the A fragments are the same chunks of the q rows (row g = query head g of
-// the group, rows 8-15 zero). K chunks are stored XOR-swizzled (bit 2 of the chunk index flipped on odd keys) so the
-// fragment reads are bank-conflict free. P*V stays on the FMA pipe: lane <-> 4 channels, probabilities broadcast from
-// shared memory.
+// Both contractions run on warp-level tensor cores (m16n8k16, M rows = the G query heads of the group, rows 8-15 idle):
+//   S = q K^T : the contraction index d may be permuted freely as long as q and k use the same permutation, so lane
+//               (g = lane/4, j = lane%4) takes the 16-byte chunks j, j+4, j+8, j+12 of "its" key row as the B fragments
+//               of two MMAs each; the A fragments are the same chunks of the q rows. No transposes.
+//   O += P V  : P is the S accumulator re-packed in registers (the FlashAttention-2 fragment identity), V fragments
+//               come from ldmatrix.trans on the row-major V tile.
+// Both tiles are stored XOR-swizzled by cp.async (16-byte chunk index ^ f(key)) so fragment reads are conflict free.
+// A thread owns head g for the softmax AND for its output fragment, so no probabilities cross lanes.
 template <int G>
 __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(128) uint8_t ring[];     // [kWarps][kStages][K tile | V tile]; reused for the merge
-  __shared__ __align__(16) float sp[kWarps][G][kBlk];  // probabilities of the warp's current key block
-  __shared__ float s_corr[kWarps][8];                  // per-head rescale of the running output for this block
   __shared__ float s_m[kWarps][G], s_l[kWarps][G];
   __shared__ __align__(16) float part_acc[G][kD];      // this CTA's (un-normalised) partial, read by cluster rank 0
   __shared__ float part_m[G], part_l[G];
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
         const int kl = (lane >> 4) + 2 * r;                       // key within the block
         const long long key = min(blk + kl, r1 - 1);
         cp_async16(st + kl * 256 + ((c ^ ((kl & 1) << 2)) << 4), kbase + key * p.ld_k + c * 8);
-        cp_async16(st + kTileBytes + kl * 256 + (c << 4), vbase + key * p.ld_v + c * 8);
+        cp_async16(st + kTileBytes + kl * 256 + ((c ^ (kl & 7)) << 4), vbase + key * p.ld_v + c * 8);
       }
     }
     cp_async_commit();   // always commit: group counting stays uniform
@@ -136,9 +142,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   }
 
   float m_run = -INFINITY, l_run = 0.f;   // state of head g (replicated over the 4 lanes j; l is a per-lane partial)
-  float acc[G][4];
+  float o[16][4];                         // O fragment: [d tile][c0, c1 = head g, channels 8*tile + 2j, +1 | c2, c3 idle]
 #pragma unroll
-  for (int h = 0; h < G; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+  for (int n = 0; n < 16; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+
+  // ldmatrix lane roles for the V fragments: matrices 0/1 = keys 0-7 / 8-15 of d tile 2x, matrices 2/3 = of d tile 2x+1
+  const int lm_key = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int lm_dsel = lane >> 4;
 
   for (int i = 0;; ++i) {
     const int blk = r0 + (warp + i * kWarps) * kBlk;
@@ -179,46 +189,25 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
     float pr[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) pr[e] = ex2f(sv[e] - m_new);   // ex2(-inf) = 0 for masked keys
-    l_run = l_run * corr + (pr[0] + pr[1]) + (pr[2] + pr[3]);
+    // P in bf16 for the tensor cores (as flash-attn does); the row sum uses the same rounded values
+    const uint32_t pa0 = pack_bf16x2(pr[0], pr[1]), pa2 = pack_bf16x2(pr[2], pr[3]);
+    l_run = l_run * corr + (bf16_lo(pa0) + bf16_hi(pa0)) + (bf16_lo(pa2) + bf16_hi(pa2));
     m_run = m_new;
-    if (g < G) {
-      *reinterpret_cast<float2*>(&sp[warp][g][2 * j]) = make_float2(pr[0], pr[1]);
-      *reinterpret_cast<float2*>(&sp[warp][g][8 + 2 * j]) = make_float2(pr[2], pr[3]);
-      if (j == 0) s_corr[warp][g] = corr;
-    }
-    __syncwarp();
-    // ---- O = O * corr + P V: lane <-> 4 consecutive channels ----
+
+    // ---- O = O * corr + P V: 16 channel tiles, V fragments by ldmatrix.trans ----
+    const uint32_t vt = st + kTileBytes + lm_key * 256;
 #pragma unroll
-    for (int h = 0; h < G; ++h) {
-      const float c = s_corr[warp][h];
-      acc[h][0] *= c; acc[h][1] *= c; acc[h][2] *= c; acc[h][3] *= c;
-    }
-    const int nrows = min(kBlk, r1 - blk);
+    for (int x = 0; x < 8; ++x) {
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, vt + (((2 * x + lm_dsel) ^ (lm_key & 7)) << 4));
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (half * 8 >= nrows) break;
-      float v0[8], v1[8], v2[8], v3[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        uint32_t x, y;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(st + kTileBytes + (half * 8 + r) * 256 + lane * 8));
-        v0[r] = bf16_lo(x); v1[r] = bf16_hi(x); v2[r] = bf16_lo(y); v3[r] = bf16_hi(y);
-      }
-#pragma unroll
-      for (int h = 0; h < G; ++h) {
-        const float4 pa = *reinterpret_cast<const float4*>(&sp[warp][h][half * 8]);
-        const float4 pb = *reinterpret_cast<const float4*>(&sp[warp][h][half * 8 + 4]);
-        const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          acc[h][0] = fmaf(pj[r], v0[r], acc[h][0]);
-          acc[h][1] = fmaf(pj[r], v1[r], acc[h][1]);
-          acc[h][2] = fmaf(pj[r], v2[r], acc[h][2]);
-          acc[h][3] = fmaf(pj[r], v3[r], acc[h][3]);
-        }
+      for (int h2 = 0; h2 < 2; ++h2) {
+        float (&acc)[4] = o[2 * x + h2];
+        acc[0] *= corr; acc[1] *= corr;
+        mma_bf16_16816(acc, pa0, 0u, pa2, 0u, vb[2 * h2], vb[2 * h2 + 1]);
       }
     }
-    __syncwarp();   // sp / s_corr and this ring stage are rewritten by the next iterations
+    __syncwarp();   // this ring stage is rewritten by a later cp.async
   }
   cp_async_wait<0>();
   __syncthreads();  // every warp is done with its ring: the merge buffers alias it
@@ -226,13 +215,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   // ---- merge: lanes -> warp -> CTA ----
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-  if (g < G && j == 0) {
-    s_m[warp][g] = m_run;
-    s_l[warp][g] = l_run;
-  }
+  if (g < G) {
+    if (j == 0) {
+      s_m[warp][g] = m_run;
+      s_l[warp][g] = l_run;
+    }
 #pragma unroll
-  for (int h = 0; h < G; ++h)
-    *reinterpret_cast<float4*>(&s_acc[warp][h][lane * 4]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    for (int n = 0; n < 16; ++n)
+      *reinterpret_cast<float2*>(&s_acc[warp][g][n * 8 + 2 * j]) = make_float2(o[n][0], o[n][1]);
+  }
   __syncthreads();
 #pragma unroll
   for (int h = 0; h < G; ++h) {
@@ -269,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
         L = fmaf(lr, wt, L);
         A = fmaf(ar, wt, A);
       }
-      const float o = (L > 0.f) ? A / L : 0.f;
-      p.out[(long long)q_row * p.ld_out + (hk * G + h) * kD + t] = __float2bfloat16_rn(o);
+      const float ov = (L > 0.f) ? A / L : 0.f;
+      p.out[(long long)q_row * p.ld_out + (hk * G + h) * kD + t] = __float2bfloat16_rn(ov);
     }
   }
   if (p.split > 1) cluster_sync_all();   // peers keep their shared memory alive until rank 0 has read it

@@ -58,3 +58,69 @@ def test_cfg_branch_batching_equals_sequential_reference_semantics(model):
     d_guided = (guided[0] - base[0]).abs().max().item()
     assert d_near < 5e-2, d_near
     assert d_guided > 10 * max(d_near, 1e-4), (d_guided, d_near)
+
+
+def test_7b_layer_dims_generate_image_vs_oracle():
+    """BAGEL-7B layer dimensions (hidden 3584, 28:4 heads x 128, MLP 18944, MoT und+gen experts), 2 layers, against
+    the oracle itself — not only through properties: text prefill -> 3-evaluation rectified-flow run with text CFG,
+    B=2 ragged images (256x256 and 192x256 -> 256 + 192 latent tokens) so the oracle (bf16 restatement AND the exact
+    fp32 evaluation) finishes in about a minute on the host. Criterion as in tests/test_gpu_model.py::_check:
+    (1) within a stated number of bf16 ulps of the tensor scale of the reference-equivalent bf16 result,
+    (2) no further from the fp32 truth than 1.5x (mean) / 2.5x (max) the bf16 restatement itself."""
+    import helpers
+    from bagel_b200.qwen2_navit import NaiveCache
+    from oracle import bagel_flow as obf, fixtures, qwen2_mot as om
+    from test_gpu_model import _check, _f32
+
+    cfg = om.LMConfig(hidden_size=3584, intermediate_size=18944, num_hidden_layers=2, num_attention_heads=28,
+                      num_key_value_heads=4, vocab_size=2048)
+    sizes = [(256, 256), (192, 256)]
+    sd = {"language_model." + k: v for k, v in fixtures.lm_state_dict(cfg, seed=11, w_std=0.02).items()}
+    sd.update(fixtures.bagel_extra_state_dict(cfg.hidden_size, seed=12))
+    sd["latent_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 16).to(torch.bfloat16)
+    model = helpers.build_product_bagel(cfg, "cuda", max_latent_size=16, load=False)
+    model.load_state_dict(sd)
+    tok = helpers.IntTokenizer()
+
+    def ctx(with_text):
+        c, kv, rp = NaiveCache(cfg.num_hidden_layers), [0, 0], [0, 0]
+        if with_text:
+            gi_, kv, rp = model.prepare_prompts(kv, rp, helpers.PROMPTS, tok, helpers.NEW_TOKEN_IDS)
+            c = model.forward_cache_update_text(c, **gi_)
+        return c, kv, rp
+
+    c_main, kv_m, rp_m = ctx(True)
+    c_txt, kv_t, rp_t = ctx(False)
+    torch.manual_seed(4)
+    gi = model.prepare_vae_latent(kv_m, rp_m, sizes, helpers.NEW_TOKEN_IDS)
+    ct = model.prepare_vae_latent_cfg(kv_t, rp_t, sizes)
+    kw = dict(num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type="global", cfg_interval=[0.4, 1.0],
+              cfg_text_scale=2.0)
+    lat = model.generate_image(
+        past_key_values=c_main, **gi, **kw,
+        cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+        cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+        cfg_text_past_key_values=c_txt)
+    torch.cuda.synchronize()
+    assert [tuple(x.shape) for x in lat] == [(256, 64), (192, 64)]
+    got = torch.cat(lat, 0).cpu()
+
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=16)
+
+    def oracle_run(sd_):
+        def octx(with_text):
+            c, kvv, rpp = om.KVCache(cfg.num_hidden_layers), [0, 0], [0, 0]
+            if with_text:
+                g_, kvv, rpp = obf.prepare_prompts(kvv, rpp, [tok.encode(p) for p in helpers.PROMPTS], 1000, 1001)
+                c = obf.forward_cache_update_text(sd_, fc, c, **g_)
+            return c
+        br = dict(packed_position_ids=ct["cfg_packed_position_ids"], packed_query_indexes=ct["cfg_packed_query_indexes"],
+                  key_values_lens=ct["cfg_key_values_lens"], past_key_values=octx(False),
+                  packed_key_value_indexes=ct["cfg_packed_key_value_indexes"])
+        return torch.cat(obf.generate_image(sd_, fc, gi, octx(True), cfg_text=br, **kw), 0)
+
+    with torch.no_grad():
+        ref = oracle_run(sd)                       # bf16 restatement == the reference's own arithmetic on the host
+        with om.high_precision():
+            truth = oracle_run(_f32(sd))           # exact fp32 evaluation of the same network
+    _check("latents[7B dims, 2 layers]", got, ref, truth, max_ulps_of_scale=8.0)
