@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   __shared__ float part_m[G], part_l[G];
   float (*s_acc)[G][kD] = reinterpret_cast<float (*)[G][kD]>(ring);   // [kWarps][G][kD], valid after the key loop
 
+  pdl_launch_dependents();   // the o_proj GEMM behind this kernel may begin prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
   const int g = lane >> 2, j = lane & 3;
   const int rank = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(128)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w0,
                const __nv_bfloat16* __restrict__ w1, const uint8_t* __restrict__ expert,
                __nv_bfloat16* __restrict__ y, long long ldy, int N, int H, float eps) {
+  pdl_launch_dependents();   // a following PDL kernel (skinny GEMM) may begin prefetching its weights
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;

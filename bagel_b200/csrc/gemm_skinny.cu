@@ -112,11 +112,23 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();   // the next PDL kernel may start its own weight prefetch while this one streams
+
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      // The weights do not depend on the kernel in front of this one: fill the (empty) ring with W tiles right away,
+      // resolve the grid dependency, then add the token tiles of the same stages (same mbarrier, one expect_tx).
+      const int npre = min(p.stages, kb_end - kb_begin);
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full_bar[i], (uint32_t)stage_bytes);
+        tma_load_2d(smem + i * stage_bytes, &tmW, &full_bar[i], (kb_begin + i) * kBK, tile * (NW * 128), kEvictFirst);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i)
+        tma_load_2d(smem + i * stage_bytes + kWBytes, &tmA, &full_bar[i], (kb_begin + i) * kBK, 0, kEvictLast);
+      int stage = (npre == p.stages) ? 0 : npre;
+      uint32_t phase = (npre == p.stages) ? 1u : 0u;
+      for (int kb = kb_begin + npre; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
         uint8_t* st = smem + stage * stage_bytes;
@@ -151,6 +163,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     __syncwarp();
   } else {
     // epilogue warps: wait for this CTA's accumulator; non-leader CTAs of a split park it in shared memory
+    pdl_wait();   // residual reads / output writes below must follow the predecessor kernel
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if (p.split > 1 && rank != 0) {
@@ -238,13 +251,17 @@ int launch(const CUtensorMap& tmW, const CUtensorMap& tmA, const SkinnyParams& p
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1;
   at[0].val.clusterDim.y = (unsigned)p.split;
   at[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: this kernel's weight prefetch overlaps the tail of whatever runs in front of it
+  static const bool pdl = [] { const char* e = getenv("BAGEL_PDL"); return !(e && atoi(e) == 0); }();
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   BAGEL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -296,7 +313,8 @@ int gemm_skinny(const void* A, long long lda, const void* W, long long ldw, void
 
   const int stage_bytes = nw * 128 * kBK * 2 + p.MT * kBK * 2;
   const long long ctas = (long long)tiles * split;
-  const int budget = (split > 1) ? 4 * stage_bytes : ((ctas <= sms) ? 148 * 1024 : 108 * 1024);
+  // <= ~110 KB per CTA also lets the NEXT kernel's CTAs (PDL weight prefetch) become resident beside this one's
+  const int budget = (split > 1) ? 4 * stage_bytes : 110 * 1024;
   int stages = budget / stage_bytes;
   if (env_stages > 0) stages = env_stages;
   if (stages > kMaxStages) stages = kMaxStages;
