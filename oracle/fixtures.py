@@ -191,3 +191,32 @@ def vae_inputs(seed: int = 8):
     img = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1          # ragged-vs-tile shape: W=48 is not a power of two
     noise = torch.randn(2, 16, 16, 24, generator=g)
     return img, noise
+
+
+class ToyTokenizer:
+    """Deterministic offline tokenizer for the inferencer tests (no vocab files offline): an integer word below 1000
+    maps to itself, any other whitespace-separated word to a stable id in [0, 900) (NOT Python's salted hash()); ids
+    1000-1003 decode to the special-token strings inferencer.gen_text splits on (reference inferencer.py:203-204)."""
+    SPECIAL = {1000: "<|im_start|>", 1001: "<|im_end|>", 1002: "<|vision_start|>", 1003: "<|vision_end|>"}
+
+    def encode(self, text):
+        ids = []
+        for w in text.split():
+            if w.isdigit() and int(w) < 1000:
+                ids.append(int(w))
+            else:
+                ids.append(sum(w.encode("utf-8")) * 7 % 900)
+        return ids
+
+    def decode(self, ids):
+        return " ".join(self.SPECIAL.get(int(i), str(int(i))) for i in ids)
+
+
+def inferencer_image(seed: int = 3, h: int = 40, w: int = 56):
+    """Synthetic RGB input image for the image-edit / understanding flows (smooth gradients + noise), as a PIL image."""
+    import numpy as np
+    from PIL import Image
+    rs = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
+    img = np.stack([xx, yy, 0.5 + 0.5 * np.sin(6 * xx * yy)], -1) * 200 + rs.randint(0, 55, (h, w, 3))
+    return Image.fromarray(img.clip(0, 255).astype(np.uint8))

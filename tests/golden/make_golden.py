@@ -389,6 +389,77 @@ def golden_vae(ns):
     save_file(out, os.path.join(OUT, "vae_tiny.safetensors"))
 
 
+def golden_inferencer(ns):
+    """InterleaveInferencer end to end (reference inferencer.py:23-313) on a tiny LM + SigLIP tower + VAE:
+    text->image, image+text->image (edit: VAE + ViT context, 3 CFG contexts), image+text->text (understanding),
+    think->image (system prompt, generated text fed back as context). The reference's
+    `torch.autocast(device_type="cuda")` block is inert on this CPU-only container, so the calls run under CPU autocast
+    like every other fixture; DiagonalGaussian sampling is switched off (the noise draw is not reproducible)."""
+    import numpy as np
+    import warnings
+    import data.transforms as rtf
+    assert ns.inferencer is not None, getattr(ns, "inferencer_error", None)
+    cfg, dtype, tv = fixtures.TINY_LM, torch.bfloat16, fixtures.TINY_VIT
+    sd = flow_state_dict(cfg, dtype)
+    sd.update(fixtures.vit_state_dict(tv["hidden"], tv["inter"], tv["layers"], tv["heads"], cfg.hidden_size, dtype=dtype))
+    lm_sd = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+    lm, rcfg = ref_lm(ns, cfg, lm_sd, dtype)
+    sn = ns.siglip_navit
+    vcfg = sn.SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                                 num_attention_heads=tv["heads"], num_channels=3, image_size=112, patch_size=14, rope=False)
+    vit = sn.SiglipVisionModel(vcfg)
+    vit.vision_model.embeddings.convert_conv2d_to_linear(vcfg)
+    bcfg = ns.bagel.BagelConfig(visual_gen=True, visual_und=True, llm_config=rcfg, vit_config=vcfg,
+                                vae_config=SimpleNamespace(downsample=2, z_channels=16), latent_patch_size=2,
+                                max_latent_size=16, vit_max_num_patch_per_side=8)
+    model = ns.bagel.Bagel(lm, vit, bcfg).eval()
+    ref_shims.cast_parameters(model, dtype)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("pos_embed" in k for k in missing.missing_keys), missing
+    ae_mod = ns.autoencoder
+    params = ae_mod.AutoEncoderParams(resolution=32, in_channels=3, downsample=2, ch=128, out_ch=3, ch_mult=[1, 2],
+                                      num_res_blocks=1, z_channels=16, scale_factor=0.3611, shift_factor=0.1159)
+    ae = ae_mod.AutoEncoder(params).eval()
+    ae.load_state_dict(fixtures.vae_state_dict(), strict=True)
+    ae.reg.sample = False
+    tok = fixtures.ToyTokenizer()
+    inf = ns.inferencer.InterleaveInferencer(model, ae, tok, rtf.ImageTransform(64, 32, 4), rtf.ImageTransform(112, 56, 14),
+                                             NEW_TOKEN_IDS)
+    img = fixtures.inferencer_image()
+    text = "5 17 900 33 2"
+    kw = dict(num_timesteps=4, timestep_shift=3.0, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=[0.4, 1.0],
+              cfg_renorm_min=0.0, cfg_renorm_type="global")
+    out = {"input.image": torch.from_numpy(np.asarray(img).copy())}
+
+    def enc(s):
+        return torch.tensor(list(s.encode("utf-8")), dtype=torch.uint8)
+
+    def run(seed, **call):
+        torch.manual_seed(seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                r = inf(**call)
+        # the reference leaves these set after an enable_taylorseer call; not used here, but keep the model clean
+        return r
+
+    r = run(21, text=text, image_shapes=(32, 48), **kw)
+    out["t2i.image"] = torch.from_numpy(np.asarray(r["image"]).copy())
+    r = run(22, image=img, text=text, **kw)
+    out["edit.image"] = torch.from_numpy(np.asarray(r["image"]).copy())
+    r = run(23, image=img, text=text, understanding_output=True, max_think_token_n=6, do_sample=False)
+    out["und.text"] = enc(r["text"])
+    r = run(24, text=text, think=True, max_think_token_n=5, do_sample=False, image_shapes=(32, 48), **kw)
+    out["think.text"] = enc(r["text"])
+    out["think.image"] = torch.from_numpy(np.asarray(r["image"]).copy())
+    for k in ("t2i.image", "edit.image", "think.image"):
+        print(f"inferencer[{k}]: shape {tuple(out[k].shape)}, mean level {out[k].float().mean():.1f}, "
+              f"std {out[k].float().std():.1f}")
+    print("inferencer[und.text]:", bytes(out["und.text"].tolist()).decode(), "| think.text:",
+          bytes(out["think.text"].tolist()).decode())
+    save_file(out, os.path.join(OUT, "inferencer_tiny.safetensors"))
+
+
 def fc_of(cfg):
     return obf.FlowConfig(lm=cfg, max_latent_size=8)
 
@@ -402,6 +473,7 @@ def main():
     golden_flow(ns)
     golden_vit(ns)
     golden_vae(ns)
+    golden_inferencer(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

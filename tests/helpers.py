@@ -60,7 +60,7 @@ def vit_flow_state_dict(cfg=fixtures.TINY_LM, dtype=torch.bfloat16, max_latent_s
     return sd
 
 
-def build_product_bagel_with_vit(cfg=fixtures.TINY_LM, device="cuda", load=True):
+def build_product_bagel_with_vit(cfg=fixtures.TINY_LM, device="cuda", load=True, max_latent_size=8, vae_downsample=8):
     from bagel_b200.bagel import Bagel
     from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config, SiglipVisionConfig
     from bagel_b200.qwen2_navit import Qwen2ForCausalLM
@@ -74,9 +74,9 @@ def build_product_bagel_with_vit(cfg=fixtures.TINY_LM, device="cuda", load=True)
     vcfg = SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
                               num_attention_heads=tv["heads"], num_channels=3, image_size=112, patch_size=14, rope=False)
     bcfg = BagelConfig(visual_gen=True, visual_und=True, llm_config=llm, vit_config=vcfg,
-                       vae_config=AutoEncoderParams(), latent_patch_size=2, max_latent_size=8,
-                       vit_max_num_patch_per_side=8)
+                       vae_config=AutoEncoderParams(downsample=vae_downsample), latent_patch_size=2,
+                       max_latent_size=max_latent_size, vit_max_num_patch_per_side=8)
     model = Bagel(Qwen2ForCausalLM(llm, device=device), SiglipVisionModel(vcfg, device=device), bcfg)
     if load:
-        model.load_state_dict(vit_flow_state_dict(cfg))
+        model.load_state_dict(vit_flow_state_dict(cfg, max_latent_size=max_latent_size))
     return model
