@@ -352,3 +352,58 @@ def test_generate_text_graph_vs_eager_and_eos(g_flow):
     model.generate_text(past_key_values=c_main, max_length=3, do_sample=True, temperature=0.7, **gs)
     for li in range(cfg.num_hidden_layers):
         assert torch.equal(snap.key_cache[li], c_main.key_cache[li])
+
+
+def test_hf_style_loader_equals_direct_construction(tmp_path):
+    """loader.load_bagel on a checkpoint directory laid out like the reference's (llm_config.json, vit_config.json,
+    ema.safetensors; app.py:39-133) must build the same model as loading the state dict directly: identical K cache of
+    a text + ViT prefill (same kernels, same fused layouts -> bit-identical)."""
+    import json
+    from safetensors.torch import save_file
+    from bagel_b200.loader import load_bagel
+    cfg, tv = fixtures.TINY_LM, fixtures.TINY_VIT
+    sd = helpers.vit_flow_state_dict(cfg, max_latent_size=64)
+    sd["vit_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 70).to(torch.bfloat16)   # loader fixes 70 / 64
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "ema.safetensors"))
+    (tmp_path / "llm_config.json").write_text(json.dumps(dict(
+        model_type="qwen2", vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+        num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta, rms_norm_eps=cfg.rms_norm_eps,
+        tie_word_embeddings=True)))
+    (tmp_path / "vit_config.json").write_text(json.dumps(dict(
+        model_type="siglip_vision_model", hidden_size=tv["hidden"], intermediate_size=tv["inter"],
+        num_hidden_layers=tv["layers"] + 1, num_attention_heads=tv["heads"], num_channels=3, image_size=980, patch_size=14)))
+    model, vae, bcfg = load_bagel(str(tmp_path), device="cuda")
+    assert bcfg.vit_config.num_hidden_layers == tv["layers"] and bcfg.llm_config.layer_module == "Qwen2MoTDecoderLayer"
+    assert vae is not None and model.vit_model is not None
+
+    from bagel_b200.bagel import Bagel
+    from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config, SiglipVisionConfig
+    from bagel_b200.qwen2_navit import NaiveCache, Qwen2ForCausalLM
+    from bagel_b200.siglip_navit import SiglipVisionModel
+    llm = Qwen2Config(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                      num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                      num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta, rms_norm_eps=cfg.rms_norm_eps,
+                      qk_norm=True, layer_module="Qwen2MoTDecoderLayer")
+    vcfg = SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                              num_attention_heads=tv["heads"], num_channels=3, image_size=980, patch_size=14, rope=False)
+    direct = Bagel(Qwen2ForCausalLM(llm, device="cuda"), SiglipVisionModel(vcfg, device="cuda"),
+                   BagelConfig(visual_gen=True, visual_und=True, llm_config=llm, vit_config=vcfg,
+                               vae_config=AutoEncoderParams(), latent_patch_size=2, max_latent_size=64,
+                               vit_max_num_patch_per_side=70))
+    direct.load_state_dict(sd)
+
+    def prefill(m):
+        tok = helpers.IntTokenizer()
+        c, kv, rp = NaiveCache(cfg.num_hidden_layers), [0, 0], [0, 0]
+        gi, kv, rp = m.prepare_vit_images(kv, rp, fixtures.vit_images(), lambda im: im, helpers.NEW_TOKEN_IDS)
+        c = m.forward_cache_update_vit(c, **gi)
+        gi, kv, rp = m.prepare_prompts(kv, rp, helpers.PROMPTS, tok, helpers.NEW_TOKEN_IDS)
+        c = m.forward_cache_update_text(c, **gi)
+        return c, kv, rp
+
+    ca, kva, rpa = prefill(model)
+    cb, kvb, rpb = prefill(direct)
+    assert kva == kvb and rpa == rpb
+    for li in range(cfg.num_hidden_layers):
+        assert torch.equal(ca.key_cache[li], cb.key_cache[li]) and torch.equal(ca.value_cache[li], cb.value_cache[li])
