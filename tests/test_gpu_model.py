@@ -362,8 +362,9 @@ def test_hf_style_loader_equals_direct_construction(tmp_path):
     from safetensors.torch import save_file
     from bagel_b200.loader import load_bagel
     cfg, tv = fixtures.TINY_LM, fixtures.TINY_VIT
-    sd = helpers.vit_flow_state_dict(cfg, max_latent_size=64)
-    sd["vit_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 70).to(torch.bfloat16)   # loader fixes 70 / 64
+    sd = helpers.flow_state_dict(cfg, max_latent_size=64)                  # the loader fixes 64 latent / 70 ViT positions
+    sd.update(fixtures.vit_state_dict(tv["hidden"], tv["inter"], tv["layers"], tv["heads"], cfg.hidden_size, max_side=70))
+    sd["vit_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 70).to(torch.bfloat16)
     save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "ema.safetensors"))
     (tmp_path / "llm_config.json").write_text(json.dumps(dict(
         model_type="qwen2", vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
