@@ -147,6 +147,17 @@ def cpu_reference_sample(image_size: int, threads: int):
     times = []
     with torch.no_grad():
         om.lm_forward_inference(sd, cfg, x, **kw)  # warm-up
+        # give the CPU arm its best thread count: bf16 matmuls on a 128-thread host are often faster with fewer threads
+        best_thr, best_t = threads, None
+        for thr in sorted({threads, max(1, threads // 2), max(1, threads // 4), max(1, threads // 8)}, reverse=True):
+            torch.set_num_threads(thr)
+            t0 = time.time()
+            om.lm_forward_inference(sd, cfg, x, **kw)
+            dt = time.time() - t0
+            if best_t is None or dt < best_t:
+                best_thr, best_t = thr, dt
+        torch.set_num_threads(best_thr)
+        threads = best_thr
         t_end = time.time() + 12.0
         while len(times) < 3 or (time.time() < t_end and len(times) < 10):
             t0 = time.time()
@@ -155,9 +166,9 @@ def cpu_reference_sample(image_size: int, threads: int):
     t_layer = statistics.median(times)
     img_s = 1.0 / (t_layer * cfg7.num_hidden_layers * 2 * EVALS_PER_IMAGE)
     sample = (f"oracle (CPU port of the reference path), 1 of 28 MoT layers x 1 sample x 1 CFG branch at "
-              f"{image_size}^2 ({n} query tokens + {ctx} ctx), median of {len(times)} runs = {t_layer:.3f} s; "
-              f"images/s = 1/(t*28*98)")
-    return img_s, sample, t_layer
+              f"{image_size}^2 ({n} query tokens + {ctx} ctx), median of {len(times)} runs = {t_layer:.3f} s on "
+              f"{threads} threads (fastest of a thread-count sweep); images/s = 1/(t*28*98)")
+    return img_s, sample, t_layer, threads
 
 
 def run_reference_arm(args):
@@ -168,7 +179,7 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     vals = []
     for _ in range(max(1, min(args.steps, 3))):
-        v, sample, t_layer = cpu_reference_sample(args.image_size, threads)
+        v, sample, t_layer, used = cpu_reference_sample(args.image_size, threads)
         vals.append(v)
     v = statistics.median(vals)
     line = {
@@ -177,7 +188,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "BAGEL-7B-MoT random-init T2I 1024^2, 49 evals, text CFG (2 branches), CPU oracle port",
                    "global_batch": args.batch, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -347,8 +358,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, sample, _ = cpu_reference_sample(args.image_size, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        v, sample, _, used = cpu_reference_sample(args.image_size, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
