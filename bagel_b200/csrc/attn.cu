@@ -5,13 +5,18 @@
 //   out[Sq,Hq,D] = softmax(q k^T * scale [+ bottom-right causal mask]) v   per packed sample, GQA by Hq % Hk == 0,
 //   bf16 in / fp32 softmax + accumulation / bf16 out.
 //
-// One CTA owns TWO 128-row query tiles of one (sample, head) and sweeps the keys in blocks of 128:
-//   warps 0-3     softmax group of tile 0 (thread = row): tcgen05.ld S -> online softmax -> P (bf16) back into
-//   warps 4-7     softmax group of tile 1                  the S columns of TMEM; rescales O in TMEM when the
-//                                                          running max grows; final O / l -> global
-//   warp 8        TMA producer: Q tiles once, then K_j / V_j blocks through a kStages smem ring
-//   warp 9        MMA issuer (one lane): S_t = Q_t K_j^T  (SS, both K-major)  and  O_t += P_t V_j (TS: A = P in TMEM,
-//                 B = V MN-major) — the tensor pipe runs tile 0 while tile 1 is in softmax and vice versa
+// One CTA owns TWO 128-row query tiles of one (sample, head) and sweeps the keys in blocks of 128. With kSplit
+// threads per score row (1 or 2; W = 4*kSplit warps per tile):
+//   warps [0, W)      softmax group of tile 0: tcgen05.ld S -> online softmax -> P (bf16) back into the S columns of
+//   warps [W, 2W)     softmax group of tile 1  TMEM; rescales O in TMEM when the running max jumps; final O / l -> global.
+//                     kSplit = 2: warps w and w+4 of a group share the same 32 rows (same TMEM lane quarter) and take
+//                     the left / right half of the columns; they agree on the row maximum through shared memory and a
+//                     64-thread named barrier per block. The softmax of one tile is a serial stage between its two MMAs
+//                     (S -> P -> PV) of ~2400 cycles; kSplit = 2 was built to test whether that is an instruction-issue
+//                     limit — it is not (slower, see the launch code), so kSplit = 1 is the default.
+//   warp 2W           TMA producer: Q tiles once, then K_j / V_j blocks through a kStages smem ring
+//   warp 2W+1         MMA issuer (one lane): S_t = Q_t K_j^T  (SS, both K-major)  and  O_t += P_t V_j (TS: A = P in TMEM,
+//                     B = V MN-major) — the tensor pipe runs tile 0 while tile 1 is in softmax and vice versa
 // TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D); P_t aliases S_t columns [0,64).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -26,7 +31,7 @@
 
 namespace bagel {
 
-constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax tile 0 | softmax tile 1 | {TMA, MMA, 2 idle}
+constexpr int attn_threads(int split) { return (8 * split + 2) * 32; }  // softmax warps of both tiles + TMA + MMA
 constexpr int kBlockM = 128;  // rows per query tile (2 tiles per CTA)
 constexpr int kBlockN = 128;  // keys per block
 
@@ -46,7 +51,8 @@ template <int D>
 struct AttnCfg {
   static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
   static constexpr int kStages = (D == 128) ? 4 : 6;
-  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256;
+  static constexpr int kXchgBytes = 2 * 2 * 2 * kBlockM * 4;  // [parity][tile][half][row] fp32 row-max exchange (kSplit = 2)
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256 + kXchgBytes;
 };
 
 // packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of FMA / ADD
@@ -66,44 +72,18 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&d);
 }
 
-// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 — P is rounded to bf16,
-// eps 3.9e-3, right after): the MUFU unit runs 16 ex2/clk/SM, i.e. 2048 cycles per pair of 128x128 score tiles — the
-// same as the four MMAs of that pair — so half of the exponentials are moved off it.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23: low mantissa bits = round(x)
-  const float2 t = fadd2(x, magic);
-  const float2 xi = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = ffma2(xi, make_float2(-1.0f, -1.0f), x);  // x - round(x) in [-0.5, 0.5]
-  float2 pz = ffma2(make_float2(0.05517147481441498f, 0.05517147481441498f), f, make_float2(0.242610901594162f, 0.242610901594162f));
-  pz = ffma2(pz, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  pz = ffma2(pz, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
-  // 2^round(x): add round(x) to the exponent field ((0x4B400000 + n) << 23 == n << 23 mod 2^32)
-  float2 r;
-  r.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// Timeline instrumentation (clock64 stamps of CTA (0,0,0)) is compiled in only with -DBAGEL_ATTN_TRACE_BUILD: even
-// dormant it costs registers in the softmax loop.
-#ifdef BAGEL_ATTN_TRACE_BUILD
-#define ATTN_TRACE(slot) do { if (tr != nullptr) tr[(slot)] = clock64(); } while (0)
-#define ATTN_TRACE_PTR(expr) (expr)
-#else
-#define ATTN_TRACE(slot) do { } while (0)
-#define ATTN_TRACE_PTR(expr) (nullptr)
-#endif
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-template <int D, int kPolyMod>  // kPolyMod: every kPolyMod-th pair of exponentials runs on the FMA pipe (0 = none)
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <int D, int kSplit>  // kSplit: threads per score row (1: 8 softmax warps, 2: 16 softmax warps)
+__global__ void __launch_bounds__(attn_threads(kSplit), 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Cfg = AttnCfg<D>;
@@ -142,11 +122,14 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* p_bar = s_bar + 2;             // [2]  softmax -> MMA: P_t(j) written (and O_t rescaled)
   uint64_t* o_bar = p_bar + 2;             // [2]  MMA -> softmax: final O_t ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][2][2][kBlockM]
+  constexpr int kSoftWarps = 4 * kSplit;          // softmax warps per tile
+  constexpr int kTmaWarp = 2 * kSoftWarps, kMmaWarp = 2 * kSoftWarps + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -157,12 +140,12 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_bar[t], 1);
-      mbar_init(&p_bar[t], 4);
+      mbar_init(&p_bar[t], kSoftWarps);
       mbar_init(&o_bar[t], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -170,7 +153,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_S[2] = {tmem_base + 0, tmem_base + 128};
   const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // =========================== TMA producer ===========================
     if (lane == 0 && nblk > 0) {
       const int ntile = tile1_active ? 2 : 1;
@@ -193,7 +176,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0 && nblk > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S[128,128] = Q[128,D] K[128,D]^T
@@ -244,62 +227,64 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tc_fence_after();
         for (int t = 0; t < ntile; ++t) {
-          [[maybe_unused]] long long* tr = ATTN_TRACE_PTR(
-              (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64)
-                  ? p.trace + 2ll * 64 * 8 + t * 4 : nullptr);
-          ATTN_TRACE(j * 8 + 0);
           mbar_wait(&p_bar[t], j & 1);  // P_t(j) in TMEM, O_t rescaled
           tc_fence_after();
-          ATTN_TRACE(j * 8 + 1);
           issue_pv(t, vstage, j > 0);
-          ATTN_TRACE(j * 8 + 2);
           if (!has_next) umma_commit(&o_bar[t]);
           // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
           if (has_next) issue_qk(t, kstage);
-          ATTN_TRACE(j * 8 + 3);
         }
         umma_commit(&kv_empty[vstage]);
         if (has_next) umma_commit(&kv_empty[kstage]);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 2 * kSoftWarps) {
     // =========================== softmax / correction / epilogue ===========================
-    const int t = warp >> 2;        // which query tile this warp group serves
-    const int quarter = warp & 3;   // TMEM lane quarter accessible to this warp
+    const int t = warp / kSoftWarps;                 // which query tile this warp group serves
+    const int hf = (warp % kSoftWarps) >> 2;         // which share of the columns (0 when kSplit == 1)
+    const int quarter = warp & 3;                    // TMEM lane quarter accessible to this warp
     const int row = quarter * 32 + lane;
     const int qi = q0 + t * kBlockM + row;  // query index within the sample
     const bool active = (t == 0) || tile1_active;
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    const uint32_t tS = tmem_S[t] + lane_off;
-    const uint32_t tO = tmem_O[t] + lane_off;
+    constexpr int NC = kBlockN / kSplit;             // score columns per thread
+    constexpr int DO = D / kSplit;                   // output columns per thread
+    const uint32_t tS = tmem_S[t] + lane_off + hf * NC;
+    const uint32_t tP = tmem_S[t] + lane_off + hf * (NC / 2);   // packed bf16 probabilities of these columns
+    const uint32_t tO = tmem_O[t] + lane_off + hf * DO;
+    const int pair_bar = 1 + t * 4 + quarter;        // named barrier shared by the kSplit warps of one row quarter
 
     if (active) {
       float m = -INFINITY, l = 0.f;
-      // trace layout: [t][j][8] for softmax (slots 0..5), MMA uses [2][j][8] + t*4
-      [[maybe_unused]] long long* tr = ATTN_TRACE_PTR(
-          (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0)
-              ? p.trace + (long long)t * 64 * 8 : nullptr);
       // Streamed online softmax. TMEM -> register reads run at ~64 B/clk per SM (a 128x128 fp32 S tile costs as many
       // cycles as its two MMAs) and so does the MUFU for its 16K exponentials, so the two must overlap: S is read in
       // 32-column chunks, and while chunk c+1 is in flight chunk c is exponentiated against the reference maximum `m`
       // carried over from earlier blocks (lazy rescaling: p = 2^((s - m) scale) may reach 2^kLazyLog2, harmless in the
       // fp32 row sum and in bf16 P). Only if the block maximum turns out to exceed m by more than the threshold
       // (or no reference exists yet) is the block redone the classic way: move m, rescale O and l, re-read S.
+      // With kSplit = 2 the two threads of a row keep identical m (they exchange their half-row maxima every block)
+      // and separate partial row sums, merged once at the end.
       constexpr float kLazyLog2 = 8.0f;
+      // row maximum over all kSplit shares; also orders "every share has finished reading S" before the P stores
+      auto row_max_exchange = [&](float mx_local, int j) -> float {
+        if constexpr (kSplit == 1) {
+          return mx_local;
+        } else {
+          float* slot = xchg + ((j & 1) * 2 + t) * 2 * kBlockM;
+          slot[hf * kBlockM + row] = mx_local;
+          named_bar_sync(pair_bar, 64);
+          return fmaxf(mx_local, slot[(hf ^ 1) * kBlockM + row]);
+        }
+      };
       for (int j = 0; j < nblk; ++j) {
-#ifdef BAGEL_ATTN_TRACE_BUILD
-        if (tr != nullptr && j >= 64) tr = nullptr;
-#endif
-        ATTN_TRACE(j * 8 + 0);
         mbar_wait(&s_bar[t], j & 1);
         tc_fence_after();
-        ATTN_TRACE(j * 8 + 1);
-        const int kv0 = j * kBlockN;
+        const int kv0 = j * kBlockN + hf * NC;     // first key of this thread's columns
         const int tile_q_lo = q0 + t * kBlockM;
-        const bool need_mask = (kv0 + kBlockN > Lk) || (p.causal && (kv0 + kBlockN - 1 > tile_q_lo + shift));
+        const bool need_mask = (j * kBlockN + kBlockN > Lk) || (p.causal && (j * kBlockN + kBlockN - 1 > tile_q_lo + shift));
         const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
 
-        uint32_t pk[kBlockN / 2];  // packed bf16 probabilities of the whole row (stored after S is fully read)
+        uint32_t pk[NC / 2];  // packed bf16 probabilities of this thread's columns (stored after S is fully read)
         float mx = -INFINITY;
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
@@ -317,9 +302,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             if (track_max) cm[i & 3] = fmaxf(cm[i & 3], fmaxf(x0, x1));
             const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
-            float2 e;
-            if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == (kPolyMod - 1)) e = ex2_poly2(x);
-            else e = make_float2(ex2(x.x), ex2(x.y));
+            const float2 e = make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
             pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
           }
@@ -328,45 +311,43 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         // warp-uniform (tcgen05.ld is .sync.aligned): the streamed path needs a reference maximum in every row of the warp
         const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);
-        bool redo;
         if (have_ref) {
           const float neg_ms = -m * p.scale_log2;
           uint32_t va[32], vb[32];
           tmem_ld_x32(tS + 0, va);
           tmem_ld_wait();
-          tmem_ld_x32(tS + 32, vb);
-          process(va, 0, neg_ms, true);
-          tmem_ld_wait();
-          tmem_ld_x32(tS + 64, va);
-          process(vb, 1, neg_ms, true);
-          tmem_ld_wait();
-          tmem_ld_x32(tS + 96, vb);
-          process(va, 2, neg_ms, true);
-          tmem_ld_wait();
-          process(vb, 3, neg_ms, true);
-          redo = (mx - m) * p.scale_log2 > kLazyLog2;
+#pragma unroll
+          for (int c = 0; c < NC / 32; c += 2) {
+            if (c + 1 < NC / 32) tmem_ld_x32(tS + (c + 1) * 32, vb);
+            process(va, c, neg_ms, true);
+            if (c + 1 < NC / 32) {
+              tmem_ld_wait();
+              if (c + 2 < NC / 32) tmem_ld_x32(tS + (c + 2) * 32, va);
+              process(vb, c + 1, neg_ms, true);
+              if (c + 2 < NC / 32) tmem_ld_wait();
+            }
+          }
         } else {
-          redo = true;
+          // no pass A can run: find this thread's block maximum first (warp-uniform: all rows of a tile start together)
+#pragma unroll 1
+          for (int c = 0; c < NC / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(tS + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = __uint_as_float(v[i]);
+              if (need_mask && (kv0 + c * 32 + i > lim)) x = -INFINITY;
+              mx = fmaxf(mx, x);
+            }
+          }
         }
-        ATTN_TRACE(j * 8 + 2);
+        mx = row_max_exchange(mx, j);      // identical in every share of the row from here on
+        const bool redo = !have_ref || ((mx - m) * p.scale_log2 > kLazyLog2);
         float alpha = 1.0f;
         if (__any_sync(0xffffffffu, redo)) {
           // slow path (first block of a row, or a jump of the maximum): classic two-pass on a re-read of S,
           // one 32-column chunk in registers at a time (rare, so latency matters less than register pressure)
-          if (!have_ref) {  // no pass A ran: find the block maximum first (warp-uniform: all rows start together)
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tS + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(v[i]);
-                if (need_mask && (kv0 + c * 32 + i > lim)) x = -INFINITY;
-                mx = fmaxf(mx, x);
-              }
-            }
-          }
           float neg_ms = -m * p.scale_log2;
           if (redo) {
             const float m_new = fmaxf(m, mx);
@@ -378,7 +359,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             rs2[1] = make_float2(0.f, 0.f);
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {  // all lanes load (sync.aligned); only the rows that moved recompute
+          for (int c = 0; c < NC / 32; ++c) {  // all lanes load (sync.aligned); only the rows that moved recompute
             uint32_t v[32];
             tmem_ld_x32(tS + c * 32, v);
             tmem_ld_wait();
@@ -386,7 +367,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
+            for (int c = 0; c < DO / 32; ++c) {
               uint32_t v[32];
               tmem_ld_x32(tO + c * 32, v);
               tmem_ld_wait();
@@ -395,33 +376,38 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               tmem_st_x32(tO + c * 32, v);
             }
           }
+          // the other share re-read S too: its reads must be over before P lands on those columns
+          if constexpr (kSplit > 1) named_bar_sync(pair_bar, 64);
         }
-        ATTN_TRACE(j * 8 + 3);
         const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
         // P (bf16 pairs) over the first 64 columns of the S region: all of S has been read by now
-        tmem_st_x32(tS + 0, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-        tmem_st_x32(tS + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
-        ATTN_TRACE(j * 8 + 4);
+#pragma unroll
+        for (int c = 0; c < NC / 64; ++c)
+          tmem_st_x32(tP + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_bar[t]);
-        ATTN_TRACE(j * 8 + 5);
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
+      if constexpr (kSplit > 1) {   // total row sum = own share + the other share's (same m in both)
+        float* slot = xchg + ((nblk & 1) * 2 + t) * 2 * kBlockM;
+        slot[hf * kBlockM + row] = l;
+        named_bar_sync(pair_bar, 64);
+        l += slot[(hf ^ 1) * kBlockM + row];
+      }
       if (nblk > 0) {
         mbar_wait(&o_bar[t], 0);
         tc_fence_after();
       }
-      // rows that never saw a visible key (m still -inf) produce 0, as flash-attn does; the polynomial exp2 maps
-      // masked scores to 2^-126 instead of 0, which only matters for such rows
+      // rows that never saw a visible key (m still -inf) produce 0, as flash-attn does
       const float inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;
       const bool row_ok = qi < Lq;
-      __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D;
+      __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D + hf * DO;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < DO / 32; ++c) {
         uint32_t v[32];
         if (nblk > 0) {
           tmem_ld_x32(tO + c * 32, v);
@@ -447,24 +433,24 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <int D, int kPolyMod>
+template <int D, int kSplit>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
                        int B, int max_seqlen_q, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  auto kern = attn_varlen_kernel<D, kPolyMod>;
+  auto kern = attn_varlen_kernel<D, kSplit>;
   static bool attr_done = false;
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   dim3 grid((max_seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM), p.Hq, B);
-  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, attn_threads(kSplit), Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -511,19 +497,14 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.trace = nullptr;
-  if (const char* e = getenv("BAGEL_ATTN_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // debug only
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // BAGEL_ATTN_POLY = 0 (all exponentials on the MUFU, default), 2/3/4 (every n-th pair on the FMA pipe): A/B knob —
-  // measured neutral-to-slower on B200 (profiles/r01_attn_poly_exp_ab.txt): the kernel is not MUFU-bound
-  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 0; }();
-  if (head_dim == 128) {
-    switch (poly) {
-      case 0: return launch_attn<128, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      case 3: return launch_attn<128, 3>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      case 4: return launch_attn<128, 4>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      default: return launch_attn<128, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-    }
-  }
-  return poly == 0 ? launch_attn<64, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
-                   : launch_attn<64, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  // BAGEL_ATTN_SPLIT = threads per score row (default 1; 2 = 16 softmax warps). A/B knob: measured SLOWER on B200
+  // (denoise shape 801 vs 928 TFLOP/s, profiles/r01_attn_rowsplit_ab.txt) — the softmax stage of a tile is bound by
+  // the TMEM read/write port and the MUFU, which more warps do not widen, not by per-warp instruction issue.
+  static const int split = [] { const char* e = getenv("BAGEL_ATTN_SPLIT"); return e ? atoi(e) : 1; }();
+  if (head_dim == 128)
+    return split == 1 ? launch_attn<128, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
+                      : launch_attn<128, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  return split == 1 ? launch_attn<64, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
+                    : launch_attn<64, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
 }
