@@ -44,7 +44,6 @@ struct AttnParams {
   int Hq, Hk;
   int causal;
   float scale_log2;  // softmax_scale * log2(e)
-  long long* trace;  // debug: per-phase clock64 stamps of CTA (0,0,0) (BAGEL_ATTN_TRACE), else null
 };
 
 template <int D>
@@ -496,7 +495,6 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.Hk = num_heads_k;
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.trace = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // BAGEL_ATTN_SPLIT = threads per score row (default 1; 2 = 16 softmax warps). A/B knob: measured SLOWER on B200
   // (denoise shape 801 vs 928 TFLOP/s, profiles/r01_attn_rowsplit_ab.txt) — the softmax stage of a tile is bound by
