@@ -25,6 +25,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "attn_decode.h"
@@ -50,7 +52,7 @@ template <int D>
 struct AttnCfg {
   static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
   static constexpr int kStages = (D == 128) ? 4 : 6;
-  static constexpr int kXchgBytes = 2 * 2 * 2 * kBlockM * 4;  // [parity][tile][half][row] fp32 row-max exchange (kSplit = 2)
+  static constexpr int kXchgBytes = 2 * 2 * 2 * 2 * kBlockM * 4;  // [kind][parity][tile][half][row] fp32 exchange of row sums / maxima (kSplit = 2)
   static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256 + kXchgBytes;
 };
 
@@ -255,24 +257,31 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (active) {
       float m = -INFINITY, l = 0.f;
-      // Streamed online softmax. TMEM -> register reads run at ~64 B/clk per SM (a 128x128 fp32 S tile costs as many
-      // cycles as its two MMAs) and so does the MUFU for its 16K exponentials, so the two must overlap: S is read in
-      // 32-column chunks, and while chunk c+1 is in flight chunk c is exponentiated against the reference maximum `m`
-      // carried over from earlier blocks (lazy rescaling: p = 2^((s - m) scale) may reach 2^kLazyLog2, harmless in the
-      // fp32 row sum and in bf16 P). Only if the block maximum turns out to exceed m by more than the threshold
-      // (or no reference exists yet) is the block redone the classic way: move m, rescale O and l, re-read S.
-      // With kSplit = 2 the two threads of a row keep identical m (they exchange their half-row maxima every block)
-      // and separate partial row sums, merged once at the end.
-      constexpr float kLazyLog2 = 8.0f;
-      // row maximum over all kSplit shares; also orders "every share has finished reading S" before the P stores
-      auto row_max_exchange = [&](float mx_local, int j) -> float {
+      // Streamed online softmax. The stage is bound by instruction issue (one softmax warp of each tile per scheduler),
+      // so the hot loop is pared down to 6 instructions per PAIR of scores (FFMA2 scale/shift, 2x MUFU.EX2, FADD2 row sum,
+      // F2FP pack; no masking code in interior blocks, no max tracking). S is read in 32-column chunks; while chunk c+1 is
+      // in flight chunk c is exponentiated against the reference maximum `m` carried over from earlier blocks (lazy
+      // rescaling). Only when a row has no reference yet, or the row sum shows that m has become badly stale, is the
+      // block redone the classic way: exact block maximum, move m, rescale O and l, re-read S.
+      // With kSplit = 2 the threads of a row keep identical m (they exchange sums / maxima through shared memory) and
+      // separate partial row sums, merged once at the end.
+      // Redo trigger of the streamed path: the block's row sum of p = 2^((s - m) scale). With an up-to-date m every p <= 1
+      // and the sum is <= 128; a stale m only scales p, l and O by a common power of two, which fp32 (and bf16, same
+      // exponent range) absorb without loss — so the maximum itself is NOT tracked in the hot loop (one FMNMX3 per pair
+      // of elements saved) and the block is redone exactly only when the sum says some p left the comfortable range
+      // (or overflowed: inf / NaN fail the comparison too).
+      constexpr float kRedoSum = 1073741824.0f;   // 2^30
+      // kSplit = 2: combine a per-thread value over the shares of a row; the barrier also orders "every share has
+      // finished reading S" before the P stores that follow
+      auto row_exchange = [&](float x, int j, int kind, bool is_max) -> float {
         if constexpr (kSplit == 1) {
-          return mx_local;
+          return x;
         } else {
-          float* slot = xchg + ((j & 1) * 2 + t) * 2 * kBlockM;
-          slot[hf * kBlockM + row] = mx_local;
+          float* slot = xchg + (((kind * 2 + (j & 1)) * 2 + t) * 2) * kBlockM;
+          slot[hf * kBlockM + row] = x;
           named_bar_sync(pair_bar, 64);
-          return fmaxf(mx_local, slot[(hf ^ 1) * kBlockM + row]);
+          const float y = slot[(hf ^ 1) * kBlockM + row];
+          return is_max ? fmaxf(x, y) : (x + y);
         }
       };
       for (int j = 0; j < nblk; ++j) {
@@ -284,50 +293,61 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
 
         uint32_t pk[NC / 2];  // packed bf16 probabilities of this thread's columns (stored after S is fully read)
-        float mx = -INFINITY;
         float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 
-        // pass A: stream S, exponentiate against the current reference maximum
-        auto process = [&](const uint32_t (&v)[32], int c, float neg_ms, bool track_max) {
+        // kMask is a compile-time tag: interior blocks (the vast majority) must not carry the predicated-off compare /
+        // select instructions of the masked variant — they still cost issue slots (310 of 700 per block and thread)
+        auto process_t = [&](auto mask_tag, const uint32_t (&v)[32], int c, float neg_ms) {
+          constexpr bool kMask = decltype(mask_tag)::value;
           const float2 nm2 = make_float2(neg_ms, neg_ms);
-          float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
-            if (need_mask) {
+            if constexpr (kMask) {
               if (kv0 + c * 32 + 2 * i > lim) x0 = -INFINITY;
               if (kv0 + c * 32 + 2 * i + 1 > lim) x1 = -INFINITY;
             }
-            if (track_max) cm[i & 3] = fmaxf(cm[i & 3], fmaxf(x0, x1));
             const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
             const float2 e = make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
             pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
           }
-          if (track_max) mx = fmaxf(mx, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
         };
 
         // warp-uniform (tcgen05.ld is .sync.aligned): the streamed path needs a reference maximum in every row of the warp
         const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);
+        bool redo = true;
         if (have_ref) {
           const float neg_ms = -m * p.scale_log2;
-          uint32_t va[32], vb[32];
-          tmem_ld_x32(tS + 0, va);
-          tmem_ld_wait();
+          auto stream = [&](auto mask_tag) {
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(tS + 0, va);
+            tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < NC / 32; c += 2) {
-            if (c + 1 < NC / 32) tmem_ld_x32(tS + (c + 1) * 32, vb);
-            process(va, c, neg_ms, true);
-            if (c + 1 < NC / 32) {
-              tmem_ld_wait();
-              if (c + 2 < NC / 32) tmem_ld_x32(tS + (c + 2) * 32, va);
-              process(vb, c + 1, neg_ms, true);
-              if (c + 2 < NC / 32) tmem_ld_wait();
+            for (int c = 0; c < NC / 32; c += 2) {
+              if (c + 1 < NC / 32) tmem_ld_x32(tS + (c + 1) * 32, vb);
+              process_t(mask_tag, va, c, neg_ms);
+              if (c + 1 < NC / 32) {
+                tmem_ld_wait();
+                if (c + 2 < NC / 32) tmem_ld_x32(tS + (c + 2) * 32, va);
+                process_t(mask_tag, vb, c + 1, neg_ms);
+                if (c + 2 < NC / 32) tmem_ld_wait();
+              }
             }
-          }
-        } else {
-          // no pass A can run: find this thread's block maximum first (warp-uniform: all rows of a tile start together)
+          };
+          if (need_mask) stream(std::true_type{});
+          else stream(std::false_type{});
+          const float rs_row = row_exchange((rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y), j, 0, false);
+          redo = !(rs_row <= kRedoSum);
+        } else if constexpr (kSplit > 1) {
+          named_bar_sync(pair_bar, 64);    // keep the barrier count of the two shares equal on every path
+        }
+        float alpha = 1.0f;
+        if (__any_sync(0xffffffffu, redo)) {
+          // slow path (first block of a row, or a large jump of the maximum): classic two-pass on re-reads of S, one
+          // 32-column chunk in registers at a time (rare, so latency matters less than register pressure)
+          float mx = -INFINITY;
 #pragma unroll 1
           for (int c = 0; c < NC / 32; ++c) {
             uint32_t v[32];
@@ -340,13 +360,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               mx = fmaxf(mx, x);
             }
           }
-        }
-        mx = row_max_exchange(mx, j);      // identical in every share of the row from here on
-        const bool redo = !have_ref || ((mx - m) * p.scale_log2 > kLazyLog2);
-        float alpha = 1.0f;
-        if (__any_sync(0xffffffffu, redo)) {
-          // slow path (first block of a row, or a jump of the maximum): classic two-pass on a re-read of S,
-          // one 32-column chunk in registers at a time (rare, so latency matters less than register pressure)
+          mx = row_exchange(mx, j, 1, true);     // exact block maximum of the row, identical in every share
           float neg_ms = -m * p.scale_log2;
           if (redo) {
             const float m_new = fmaxf(m, mx);
@@ -362,7 +376,10 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             uint32_t v[32];
             tmem_ld_x32(tS + c * 32, v);
             tmem_ld_wait();
-            if (redo) process(v, c, neg_ms, false);
+            if (redo) {
+              if (need_mask) process_t(std::true_type{}, v, c, neg_ms);
+              else process_t(std::false_type{}, v, c, neg_ms);
+            }
           }
           if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
 #pragma unroll
@@ -392,10 +409,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
       // ---- epilogue: O / l -> bf16 -> global ----
       if constexpr (kSplit > 1) {   // total row sum = own share + the other share's (same m in both)
-        float* slot = xchg + ((nblk & 1) * 2 + t) * 2 * kBlockM;
-        slot[hf * kBlockM + row] = l;
-        named_bar_sync(pair_bar, 64);
-        l += slot[(hf ^ 1) * kBlockM + row];
+        l = row_exchange(l, nblk, 0, false);
       }
       if (nblk > 0) {
         mbar_wait(&o_bar[t], 0);
