@@ -73,26 +73,6 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&d);
 }
 
-// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 — P is rounded to bf16,
-// eps 3.9e-3, right after). The MUFU unit of a scheduler takes 8 cycles per warp-wide ex2, i.e. 1024 cycles for the 128
-// columns one softmax warp owns: once the hot loop is lean that is its floor, so every kPoly-th pair moves to the FMA pipe.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23: low mantissa bits = round(x)
-  const float2 t = fadd2(x, magic);
-  const float2 xi = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = ffma2(xi, make_float2(-1.0f, -1.0f), x);  // x - round(x) in [-0.5, 0.5]
-  float2 pz = ffma2(make_float2(0.05517147481441498f, 0.05517147481441498f), f, make_float2(0.242610901594162f, 0.242610901594162f));
-  pz = ffma2(pz, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  pz = ffma2(pz, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
-  // 2^round(x): add round(x) to the exponent field ((0x4B400000 + n) << 23 == n << 23 mod 2^32)
-  float2 r;
-  r.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -103,7 +83,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int D, int kSplit, int kPoly>  // kSplit: threads per score row; kPoly: every kPoly-th pair of exp2 on the FMA pipe (0 = none)
+template <int D, int kSplit>  // kSplit: threads per score row (1: 8 softmax warps, 2: 16 softmax warps)
 __global__ void __launch_bounds__(attn_threads(kSplit), 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -329,9 +309,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               if (kv0 + c * 32 + 2 * i + 1 > lim) x1 = -INFINITY;
             }
             const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
-            float2 e;
-            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly - 1)) e = ex2_poly2(x);
-            else e = make_float2(ex2(x.x), ex2(x.y));
+            const float2 e = make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
             pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
           }
@@ -474,371 +452,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Half-block pipelined variant (default). Same roles and TMEM budget as attn_varlen_kernel<D, 1, 0>, but each 128-key
-// block of a tile is handled as two 64-key halves with their own S columns ([0,64) and [64,128)), barriers and P
-// region (packed bf16 over the first 32 columns of the half):
-//     softmax(lo, j) -> P_lo -> [ PV_lo(j), QK_lo(j+1) ]        while the softmax warps already work on hi(j)
-//     softmax(hi, j) -> P_hi -> [ PV_hi(j), QK_hi(j+1) ]        while they work on lo(j+1) ...
-// In attn_varlen_kernel the softmax of a tile and its two MMAs form a strictly serial chain per block (P aliases S), so
-// the tensor pipe idles for the whole softmax stage of a tile unless the other tile happens to fill it; here the S half
-// the softmax needs next has been recomputed by the time it finishes the current one, the softmax warps never wait in
-// steady state and the tensor pipe sees a continuous stream t0.lo, t1.lo, t0.hi, t1.hi.
-// O is rescaled by the softmax warps only after the previously issued P*V of the tile has completed (pv_bar).
-// ---------------------------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(attn_threads(1), 1)
-attn_varlen_kernel_h(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using Cfg = AttnCfg<D>;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kTileBytes = Cfg::kTileBytes;
-  constexpr int kAtoms = D / 64;               // 64-column (128 B) swizzle atoms per row
-  constexpr int kAtomBytes = kBlockM * 128;    // one [128 rows x 64 cols] box
-  constexpr int kHalf = kBlockN / 2;           // keys per half block
-
-  const int b = blockIdx.z;
-  const int h = blockIdx.y;
-  const int q_beg = p.cu_q[b], Lq = p.cu_q[b + 1] - q_beg;
-  const int k_beg = p.cu_k[b], Lk = p.seqused_k ? p.seqused_k[b] : (p.cu_k[b + 1] - k_beg);
-  const int q0 = blockIdx.x * 2 * kBlockM;  // first query row (within the sample) of this CTA
-  if (q0 >= Lq) return;                     // whole CTA idle (grid is sized by max_seqlen_q)
-  const bool tile1_active = (q0 + kBlockM) < Lq;
-  const int hk = h / (p.Hq / p.Hk);
-  const int shift = Lk - Lq;  // bottom-right aligned causal: key kv visible to query qi iff kv <= qi + shift
-
-  int kv_end = Lk;
-  if (p.causal) {
-    const int q_hi = min(Lq, q0 + 2 * kBlockM) - 1;
-    kv_end = max(0, min(Lk, q_hi + shift + 1));
-  }
-  const int nblk = (kv_end + kBlockN - 1) / kBlockN;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                      // 2 tiles
-  uint8_t* smem_kv = smem + 2 * kTileBytes;    // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kStages * kTileBytes);
-  uint64_t* q_bar = bars;                  // [1]
-  uint64_t* kv_full = bars + 1;            // [kStages]
-  uint64_t* kv_empty = kv_full + kStages;  // [kStages]
-  uint64_t* s_bar = kv_empty + kStages;    // [2 tiles][2 halves]  MMA -> softmax: S_t,h(j) ready
-  uint64_t* p_bar = s_bar + 4;             // [2][2]  softmax -> MMA: P_t,h(j) written (and O_t rescaled)
-  uint64_t* pv_bar = p_bar + 4;            // [2]     MMA -> softmax: one more P*V half of tile t has completed
-  uint64_t* o_bar = pv_bar + 2;            // [2]     MMA -> softmax: final O_t ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
-  constexpr int kTmaWarp = 8, kMmaWarp = 9;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_bar, 1);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_bar[i], 1);
-      mbar_init(&p_bar[i], 4);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&pv_bar[t], 1);
-      mbar_init(&o_bar[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S[2] = {tmem_base + 0, tmem_base + 128};
-  const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
-
-  if (warp == kTmaWarp) {
-    // =========================== TMA producer ===========================
-    if (lane == 0 && nblk > 0) {
-      const int ntile = tile1_active ? 2 : 1;
-      mbar_expect_tx(q_bar, ntile * kTileBytes);
-      for (int t = 0; t < ntile; ++t)
-        for (int a = 0; a < kAtoms; ++a)
-          tma_load_2d(smem_q + t * kTileBytes + a * kAtomBytes, &tmQ, q_bar, h * D + a * 64,
-                      q_beg + q0 + t * kBlockM, kEvictFirst);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          mbar_expect_tx(&kv_full[stage], kTileBytes);
-          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
-          for (int a = 0; a < kAtoms; ++a)
-            tma_load_2d(smem_kv + stage * kTileBytes + a * kAtomBytes, tm, &kv_full[stage], hk * D + a * 64,
-                        k_beg + j * kBlockN, kEvictLast);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0 && nblk > 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kHalf, 0, 0);  // S[128,64] = Q[128,D] K[64,D]^T
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, D, 0, 1);      // O[128,D] += P[128,64] V[64,D]
-      const int ntile = tile1_active ? 2 : 1;
-      int stage = 0;
-      uint32_t phase = 0;
-
-      auto issue_qk = [&](int t, int hh, int kstage) {
-        // keys [64*hh, 64*hh + 64) of the K block: 64 rows = 8 swizzle groups of 1024 B further into each atom
-#pragma unroll
-        for (int a = 0; a < kAtoms; ++a) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + t * kTileBytes + a * kAtomBytes));
-          const uint64_t b_desc =
-              umma_desc_kmajor_sw128(smem_u32(smem_kv + kstage * kTileBytes + a * kAtomBytes + hh * (kHalf * 128)));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem_S[t] + hh * kHalf, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, (a | k) != 0);
-        }
-        umma_commit(&s_bar[t * 2 + hh]);
-      };
-      auto issue_pv = [&](int t, int hh, int vstage, bool accumulate) {
-        // A = P_t,h from TMEM (bf16 pairs: 16 keys = 8 columns per UMMA_K step, first 32 columns of the half);
-        // B = V rows [64*hh, +64), MN-major: 64-col halves LBO = kAtomBytes apart, 16 keys = 2048 B
-        const uint32_t vbase = smem_u32(smem_kv + vstage * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kHalf / 16; ++k) {
-          const uint64_t b_desc = umma_desc_mnmajor_sw128(vbase + (hh * (kHalf / 16) + k) * 2048, kAtomBytes);
-          umma_ts(tmem_O[t], tmem_S[t] + hh * kHalf + k * 8, b_desc, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-        }
-        umma_commit(&pv_bar[t]);
-      };
-
-      mbar_wait(q_bar, 0);
-      mbar_wait(&kv_full[stage], phase);   // K_0
-      tc_fence_after();
-      for (int hh = 0; hh < 2; ++hh)
-        for (int t = 0; t < ntile; ++t) issue_qk(t, hh, stage);
-      umma_commit(&kv_empty[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
-
-      for (int j = 0; j < nblk; ++j) {
-        const int vstage = stage;
-        mbar_wait(&kv_full[vstage], phase);  // V_j
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-        const int kstage = stage;
-        const bool has_next = (j + 1) < nblk;
-        if (has_next) {
-          mbar_wait(&kv_full[kstage], phase);  // K_{j+1}
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        tc_fence_after();
-        for (int hh = 0; hh < 2; ++hh) {
-          for (int t = 0; t < ntile; ++t) {
-            mbar_wait(&p_bar[t * 2 + hh], j & 1);  // P_t,h(j) in TMEM, O_t rescaled if needed
-            tc_fence_after();
-            issue_pv(t, hh, vstage, (j | hh) != 0);
-            if (!has_next && hh == 1) umma_commit(&o_bar[t]);
-            // S_t,h(j+1) overwrites the columns P_t,h(j) lives in: safe, the tensor pipe executes in issue order
-            if (has_next) issue_qk(t, hh, kstage);
-          }
-        }
-        umma_commit(&kv_empty[vstage]);
-        if (has_next) umma_commit(&kv_empty[kstage]);
-      }
-    }
-  } else if (warp < 8) {
-    // =========================== softmax / correction / epilogue ===========================
-    const int t = warp >> 2;                         // which query tile this warp group serves
-    const int quarter = warp & 3;                    // TMEM lane quarter accessible to this warp
-    const int row = quarter * 32 + lane;
-    const int qi = q0 + t * kBlockM + row;  // query index within the sample
-    const bool active = (t == 0) || tile1_active;
-    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    const uint32_t tO = tmem_O[t] + lane_off;
-
-    if (active) {
-      float m = -INFINITY, l = 0.f;
-      constexpr float kRedoSum = 1073741824.0f;   // 2^30, see attn_varlen_kernel
-      const int tile_q_lo = q0 + t * kBlockM;
-      const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      int n_pv = 0;                                 // P*V halves of this tile issued so far (= halves handed over)
-      for (int j = 0; j < nblk; ++j) {
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          mbar_wait(&s_bar[t * 2 + hh], j & 1);
-          tc_fence_after();
-          const uint32_t tS = tmem_S[t] + lane_off + hh * kHalf;
-          const int kv0 = j * kBlockN + hh * kHalf;
-          const bool need_mask = (kv0 + kHalf > Lk) || (p.causal && (kv0 + kHalf - 1 > tile_q_lo + shift));
-
-          uint32_t pk[kHalf / 2];
-          float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-          auto process_t = [&](auto mask_tag, const uint32_t (&v)[32], int c, float neg_ms) {
-            constexpr bool kMask = decltype(mask_tag)::value;
-            const float2 nm2 = make_float2(neg_ms, neg_ms);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
-              if constexpr (kMask) {
-                if (kv0 + c * 32 + 2 * i > lim) x0 = -INFINITY;
-                if (kv0 + c * 32 + 2 * i + 1 > lim) x1 = -INFINITY;
-              }
-              const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
-              const float2 e = make_float2(ex2(x.x), ex2(x.y));
-              rs2[i & 1] = fadd2(rs2[i & 1], e);
-              pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
-            }
-          };
-
-          const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);
-          bool redo = true;
-          if (have_ref) {
-            const float neg_ms = -m * p.scale_log2;
-            auto stream = [&](auto mask_tag) {
-              uint32_t va[32], vb[32];
-              tmem_ld_x32(tS + 0, va);
-              tmem_ld_wait();
-              tmem_ld_x32(tS + 32, vb);
-              process_t(mask_tag, va, 0, neg_ms);
-              tmem_ld_wait();
-              process_t(mask_tag, vb, 1, neg_ms);
-            };
-            if (need_mask) stream(std::true_type{});
-            else stream(std::false_type{});
-            redo = !((rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y) <= kRedoSum);
-          }
-          float alpha = 1.0f;
-          if (__any_sync(0xffffffffu, redo)) {
-            // slow path (first half of a row, or m badly stale): exact maximum of the half, move m, rescale O and l
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kHalf / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tS + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(v[i]);
-                if (need_mask && (kv0 + c * 32 + i > lim)) x = -INFINITY;
-                mx = fmaxf(mx, x);
-              }
-            }
-            float neg_ms = -m * p.scale_log2;
-            if (redo) {
-              const float m_new = fmaxf(m, mx);
-              const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-              alpha = ex2((m - m_use) * p.scale_log2);  // m = -inf -> 0
-              m = m_new;
-              neg_ms = -m_use * p.scale_log2;
-              rs2[0] = make_float2(0.f, 0.f);
-              rs2[1] = make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int c = 0; c < kHalf / 32; ++c) {  // all lanes load (sync.aligned); only the rows that moved recompute
-              uint32_t v[32];
-              tmem_ld_x32(tS + c * 32, v);
-              tmem_ld_wait();
-              if (redo) {
-                if (need_mask) process_t(std::true_type{}, v, c, neg_ms);
-                else process_t(std::false_type{}, v, c, neg_ms);
-              }
-            }
-            if (n_pv > 0) {
-              // every P*V half of this tile issued so far must have landed in O before it is rescaled; no further one
-              // can be issued until this half's P is handed over below
-              mbar_wait(&pv_bar[t], (n_pv - 1) & 1);
-              tc_fence_after();
-#pragma unroll
-              for (int c = 0; c < D / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_x32(tO + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                tmem_st_x32(tO + c * 32, v);
-              }
-            }
-          }
-          const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
-          l = l * alpha + rs;
-          // P (bf16 pairs) over the first 32 columns of this half's S region: the half has been fully read by now
-          tmem_st_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_bar[t * 2 + hh]);
-          ++n_pv;
-        }
-      }
-
-      // ---- epilogue: O / l -> bf16 -> global ----
-      if (nblk > 0) {
-        mbar_wait(&o_bar[t], 0);
-        tc_fence_after();
-      }
-      const float inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;   // rows without any visible key produce 0
-      const bool row_ok = qi < Lq;
-      __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D;
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t v[32];
-        if (nblk > 0) {
-          tmem_ld_x32(tO + c * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2 * e]) * inv_l, __uint_as_float(v[q4 * 8 + 2 * e + 1]) * inv_l);
-            dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-template <int D>
-static int launch_attn_h(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
-                         int B, int max_seqlen_q, cudaStream_t stream) {
-  using Cfg = AttnCfg<D>;
-  auto kern = attn_varlen_kernel_h<D>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
-  dim3 grid((max_seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM), p.Hq, B);
-  kern<<<grid, attn_threads(1), Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  BAGEL_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-
-template <int D, int kSplit, int kPoly>
+template <int D, int kSplit>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
                        int B, int max_seqlen_q, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  auto kern = attn_varlen_kernel<D, kSplit, kPoly>;
+  auto kern = attn_varlen_kernel<D, kSplit>;
   static bool attr_done = false;
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -892,27 +510,13 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // BAGEL_ATTN_HALVES (default 1): half-block pipelined kernel; 0 = whole-block kernel with the A/B knobs below
-  static const int halves = [] { const char* e = getenv("BAGEL_ATTN_HALVES"); return e ? atoi(e) : 1; }();
-  if (halves)
-    return head_dim == 128 ? launch_attn_h<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
-                           : launch_attn_h<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
   // BAGEL_ATTN_SPLIT = threads per score row (default 1; 2 = 16 softmax warps). A/B knob: measured SLOWER on B200
   // (denoise shape 801 vs 928 TFLOP/s, profiles/r01_attn_rowsplit_ab.txt) — the softmax stage of a tile is bound by
   // the TMEM read/write port and the MUFU, which more warps do not widen, not by per-warp instruction issue.
   static const int split = [] { const char* e = getenv("BAGEL_ATTN_SPLIT"); return e ? atoi(e) : 1; }();
-  // BAGEL_ATTN_POLY = n: every n-th pair of exponentials on the FMA pipe (0 = all on the MUFU). A/B knob.
-  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? atoi(e) : 0; }();
-  if (head_dim == 128) {
-    if (split != 1) return launch_attn<128, 2, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-    switch (poly) {
-      case 2: return launch_attn<128, 1, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      case 3: return launch_attn<128, 1, 3>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      case 4: return launch_attn<128, 1, 4>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      case 8: return launch_attn<128, 1, 8>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-      default: return launch_attn<128, 1, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-    }
-  }
-  return split == 1 ? launch_attn<64, 1, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
-                    : launch_attn<64, 2, 0>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  if (head_dim == 128)
+    return split == 1 ? launch_attn<128, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
+                      : launch_attn<128, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  return split == 1 ? launch_attn<64, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
+                    : launch_attn<64, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
 }
