@@ -54,7 +54,12 @@ long long bagel_launch_count(void);
  *   bias     [N] bf16 or NULL.   resid  [*, ldr] bf16 (BAGEL_EPI_RESID only).
  *   row_map  optional int32[M]: A-row r is written to C row row_map[r] (and reads resid row row_map[r]);
  *            used to scatter the und-expert rows of a MoT layer back into the packed sequence.
- * K, N, lda, ldw, ldc, ldr must be multiples of 8; pointers 16-byte aligned. */
+ * K, N, lda, ldw, ldc, ldr must be multiples of 8; pointers 16-byte aligned.
+ * M <= 64 (token-by-token decode, und-expert rows) takes a weight-streaming path: swapped operands, split-K over a
+ * thread-block cluster, launched with programmatic stream serialization — its W tiles may be prefetched while the
+ * kernel in front of it on `stream` is still running (A, bias, resid and C are only touched after that kernel has
+ * completed). W must therefore not be written by the immediately preceding kernel; BAGEL_PDL=0 in the environment
+ * turns the early launch off, BAGEL_GEMM_SKINNY=0 the whole path. */
 int bagel_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                     int N, int K, const void* bias, const void* resid, long long ldr, const int* row_map,
                     int epilogue, void* stream);
