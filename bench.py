@@ -192,12 +192,31 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The driver parses ONE JSON line from stdout. Libraries print there too (NCCL's version banner under torchrun), so
+    keep a private duplicate of the real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _claim_stdout()
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -378,7 +397,7 @@ def main():
         }
         if args.layers is not None:
             line["invalid"] = "debug run with a reduced layer count"
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
