@@ -22,7 +22,7 @@ model.vit_patch_size, model.vit_max_num_patch_per_side, model.vit_hidden_size = 
 model.connector = MLPconnector(1152, 3584); model.connector.load(vsd, "connector.", dev)
 model.vit_pos_embed = PositionEmbedding(70, 3584, dev)
 
-B = 32
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 imgs = [torch.rand(3, 378, 378, generator=torch.Generator().manual_seed(3 + i)) * 2 - 1 for i in range(B)]
 tok = synthetic.RandomIdTokenizer(1)
 
