@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--image-size", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (marks the run invalid)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-no-graph", action="store_true", help="A/B: run the e2e generate_image without CUDA-graph capture")
     ap.add_argument("--no-taylorseer", action="store_true", help="skip the informational enable_taylorseer=True run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -323,7 +324,7 @@ def main():
 
     # ---------------- end to end through the public API ----------------
     e2e = None
-    model.use_cuda_graph = True
+    model.use_cuda_graph = not args.e2e_no_graph
     if not args.no_e2e:
         noise_host = gen_input["packed_init_noises"].pin_memory()
         gi = dict(gen_input)
