@@ -699,7 +699,15 @@ class FlowRunner:
         self.dts_dev = torch.tensor(dts, dtype=torch.float32, device=dev)
         self.dt_cur = torch.zeros(1, dtype=torch.float32, device=dev)
         self.t_cur = torch.zeros_like(st["t_emb"][0])
-        self.use_cuda_graph = bool(getattr(model, "use_cuda_graph", True))
+        # CUDA graphs pay off only when a step is launch-bound. Capturing ~430 launches (twice, one graph per branch
+        # set) costs ~0.7 s during which the GPU idles; at BAGEL-7B / 1024^2 / batch 8 a step is 0.8 s of GPU work
+        # behind ~20 ms of asynchronous launches, so eager replay loses nothing there (measured: 39.4 s vs 40.1 s
+        # per generate_image). Estimate the step from its linear-layer FLOPs at ~1 PFLOP/s.
+        lcfg = model.language_model.model.config
+        Hd, Id = lcfg.hidden_size, lcfg.intermediate_size
+        qkv_o = (lcfg.num_attention_heads * 2 + lcfg.num_key_value_heads * 2) * lcfg.head_dim
+        flops_step = 2.0 * nbmax * st["n"] * lcfg.num_hidden_layers * Hd * (qkv_o + 3 * Id)
+        self.use_cuda_graph = bool(getattr(model, "use_cuda_graph", True)) and flops_step / 1.0e15 < 0.05
         self._graphs: Dict[str, Any] = {}
         self._eager_done: Dict[str, int] = {}
         # TaylorSeer (reference bagel.py:680-684): one schedule per branch; factor planes of the last decoder
