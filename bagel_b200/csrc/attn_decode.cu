@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   float (*s_acc)[G][kD] = reinterpret_cast<float (*)[G][kD]>(ring);   // [kWarps][G][kD], valid after the key loop
 
   pdl_launch_dependents();   // the o_proj GEMM behind this kernel may begin prefetching its weights
-  pdl_wait();                // launched with PDL itself: q and the newest K/V row come from the kernel in front
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
   const int g = lane >> 2, j = lane & 3;
   const int rank = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -282,15 +281,13 @@ int launch(const DecodeParams& p, int Hk, int B, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kRingBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)p.split;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = 1;
   BAGEL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

@@ -29,7 +29,6 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
                const __nv_bfloat16* __restrict__ w1, const uint8_t* __restrict__ expert,
                __nv_bfloat16* __restrict__ y, long long ldy, int N, int H, float eps) {
   pdl_launch_dependents();   // a following PDL kernel (skinny GEMM) may begin prefetching its weights
-  pdl_wait();                // launched with PDL itself: x comes from the kernel in front
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -170,8 +169,6 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, con
                     __nv_bfloat16* __restrict__ q_out, long long ld_q, __nv_bfloat16* __restrict__ k_out,
                     __nv_bfloat16* __restrict__ v_out, long long ld_kv, const int* __restrict__ kv_rows, int N,
                     int Hq, int Hk, float eps, int fp32_flow) {
-  pdl_launch_dependents();
-  pdl_wait();   // launched with PDL: qkv comes from the GEMM in front
   constexpr int E = D / 64;  // elements per lane in each half
   constexpr int HALF = D / 2;
   const int row = blockIdx.x;
@@ -575,7 +572,7 @@ extern "C" int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, 
   auto W0 = static_cast<const __nv_bfloat16*>(w0);
   auto W1 = static_cast<const __nv_bfloat16*>(w1);
   auto Y = static_cast<__nv_bfloat16*>(y);
-#define RMS_CASE(V) BAGEL_CUDA_CHECK(launch_pdl(rmsnorm_kernel<V>, grid, block, 0, s, X, ldx, W0, W1, expert, Y, ldy, N, H, eps))
+#define RMS_CASE(V) rmsnorm_kernel<V><<<grid, block, 0, s>>>(X, ldx, W0, W1, expert, Y, ldy, N, H, eps)
   if (vpl <= 1) RMS_CASE(1);
   else if (vpl <= 2) RMS_CASE(2);
   else if (vpl <= 4) RMS_CASE(4);
@@ -638,8 +635,8 @@ extern "C" int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void*
       static_cast<const __nv_bfloat16*>(k_w1), expert, cos_t, sin_t, static_cast<__nv_bfloat16*>(q_out), ld_q,    \
       static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), ld_kv, kv_rows, N, Hq, Hk, eps,     \
       fp32_flow
-  if (D == 128) BAGEL_CUDA_CHECK(launch_pdl(qk_norm_rope_kernel<128>, dim3(N), dim3(128), 0, s, QK_ARGS));
-  else BAGEL_CUDA_CHECK(launch_pdl(qk_norm_rope_kernel<64>, dim3(N), dim3(128), 0, s, QK_ARGS));
+  if (D == 128) qk_norm_rope_kernel<128><<<N, 128, 0, s>>>(QK_ARGS);
+  else qk_norm_rope_kernel<64><<<N, 128, 0, s>>>(QK_ARGS);
 #undef QK_ARGS
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());

@@ -257,7 +257,7 @@ int launch(const CUtensorMap& tmW, const CUtensorMap& tmA, const SkinnyParams& p
   at[0].val.clusterDim.y = (unsigned)p.split;
   at[0].val.clusterDim.z = 1;
   // programmatic dependent launch: this kernel's weight prefetch overlaps the tail of whatever runs in front of it
-  const bool pdl = pdl_enabled();
+  static const bool pdl = [] { const char* e = getenv("BAGEL_PDL"); return !(e && atoi(e) == 0); }();
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;

@@ -5,7 +5,6 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <stdlib.h>
 
 #include <atomic>
 
@@ -26,29 +25,6 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
 // stride `stride` along W and H (strided convolutions), 128-byte swizzle, zero fill outside the tensor.
 int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
                            uint32_t box_w, uint32_t box_h, uint32_t stride);
-
-// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor on the stream
-// drains; it MUST execute pdl_wait() (common.cuh) before touching anything that predecessor produces. BAGEL_PDL=0 in
-// the environment turns the attribute off everywhere.
-inline bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("BAGEL_PDL"); return !(e && atoi(e) == 0); }();
-  return on;
-}
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
 
 #define BAGEL_CUDA_CHECK(expr)                                                                       \
   do {                                                                                               \
