@@ -41,7 +41,7 @@ print(f"[cfg3 und prefill] B={B}: {ntok} tokens ({ntok//B}/sample) in {dt*1e3:.1
 
 gs = model.prepare_start_tokens(kv, rp, synthetic.NEW_TOKEN_IDS)
 times = {}
-for steps in (4, 16, 128):
+for steps in (4, 32, 160):
     from copy import deepcopy
     c = deepcopy(cache); torch.cuda.synchronize()
     t0 = time.perf_counter(); toks = model.generate_text(past_key_values=c, max_length=steps, do_sample=False, **gs); torch.cuda.synchronize()
@@ -49,5 +49,5 @@ for steps in (4, 16, 128):
     print(f"[decode] B={B} ctx={ntok//B}: {steps} steps in {dt*1e3:.1f} ms = {dt/steps*1e3:.2f} ms/step = {B*steps/dt:.0f} tokens/s "
           f"(HBM roofline: ~14.1 GB weights/step -> 2.1 ms)", flush=True)
     times[steps] = dt
-marg = (times[128] - times[16]) / 112
-print(f"[decode] steady state (marginal over steps 16..128, CUDA-graph replay): {marg*1e3:.2f} ms/step = {B/marg:.0f} tokens/s", flush=True)
+marg = (times[160] - times[32]) / 128
+print(f"[decode] steady state (marginal over steps 32..160, CUDA-graph replay; a negative or odd value means a run hit an outlier): {marg*1e3:.2f} ms/step = {B/marg:.0f} tokens/s", flush=True)
