@@ -117,21 +117,49 @@ class Bagel:
     # weights (reference key schema)
     # ------------------------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        """Reference key schema. strict=True: every expected tensor must be present and nothing may be left over
+        (KeyError lists both); strict=False: unexpected keys are ignored, but the heads this configuration needs
+        (vae2llm / llm2vae / time_embedder for visual_gen, connector for visual_und) must still be there — a model with
+        `None` weights would only fail later inside a kernel call."""
         lm_sd = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
-        self.language_model.load_state_dict(lm_sd, strict=True)
+        unexpected = ["language_model." + k for k in self.language_model.load_state_dict(lm_sd, strict=False)]
+        used = set()
+        missing: List[str] = []
+
+        def need(keys):
+            miss = [k for k in keys if k not in sd]
+            missing.extend(miss)
+            used.update(keys)
+            return not miss
+
         if self.config.visual_gen:
-            self.time_embedder.load(sd, "time_embedder.", self.device)
-            self.vae2llm.load(sd, "vae2llm.", self.device)
-            self.llm2vae.load(sd, "llm2vae.", self.device)
-            self.latent_pos_embed.load(sd.get("latent_pos_embed.pos_embed"))
+            if need(["time_embedder.mlp.0.weight", "time_embedder.mlp.0.bias", "time_embedder.mlp.2.weight",
+                     "time_embedder.mlp.2.bias"]):
+                self.time_embedder.load(sd, "time_embedder.", self.device)
+            if need(["vae2llm.weight", "vae2llm.bias"]):
+                self.vae2llm.load(sd, "vae2llm.", self.device)
+            if need(["llm2vae.weight", "llm2vae.bias"]):
+                self.llm2vae.load(sd, "llm2vae.", self.device)
+            self.latent_pos_embed.load(sd.get("latent_pos_embed.pos_embed"))   # frozen sincos table: optional
+            used.add("latent_pos_embed.pos_embed")
         if self.config.visual_und:
-            if "connector.fc1.weight" in sd:
+            if need(["connector.fc1.weight", "connector.fc1.bias", "connector.fc2.weight", "connector.fc2.bias"]):
                 self.connector.load(sd, "connector.", self.device)
             self.vit_pos_embed.load(sd.get("vit_pos_embed.pos_embed"))
+            used.add("vit_pos_embed.pos_embed")
+            vit_sd = {k[len("vit_model."):]: v for k, v in sd.items() if k.startswith("vit_model.")}
+            used.update("vit_model." + k for k in vit_sd)
             if self.vit_model is not None and hasattr(self.vit_model, "load_state_dict"):
-                vit_sd = {k[len("vit_model."):]: v for k, v in sd.items() if k.startswith("vit_model.")}
                 if vit_sd:
                     self.vit_model.load_state_dict(vit_sd)
+                else:
+                    missing.append("vit_model.*")
+        unexpected += [k for k in sd if not k.startswith("language_model.") and k not in used]
+        if missing:
+            raise KeyError(f"bagel_b200.Bagel.load_state_dict: missing weights {missing[:12]}"
+                           + (f" (+{len(missing) - 12} more)" if len(missing) > 12 else ""))
+        if strict and unexpected:
+            raise KeyError(f"bagel_b200.Bagel.load_state_dict: unexpected keys {unexpected[:12]}")
         return self
 
     # ------------------------------------------------------------------------------------------
@@ -472,7 +500,7 @@ class Bagel:
         """Plan a whole denoising run (same arguments as generate_image); FlowRunner.step(i) then executes
         velocity evaluation + CFG + Euler update number i as a sync-free kernel sequence."""
         if cfg_renorm_type not in ops.RENORM:
-            raise NotImplementedError(f"{cfg_renorm_type} is not suppoprted")
+            raise NotImplementedError(f"{cfg_renorm_type} is not supported")
         dev = self.device
 
         # ---- schedule (host; identical arithmetic to the reference :693-696) ----
@@ -497,6 +525,10 @@ class Bagel:
                                      past_key_values=cfg_img_past_key_values, key_values_lens=cfg_img_key_values_lens,
                                      packed_key_value_indexes=cfg_img_packed_key_value_indexes))
         nbmax = len(branches)
+        # every LM workspace at its final size BEFORE the first launch / graph capture: the 'full' (all-branch) steps
+        # need nbmax*n rows, the 'main' steps n — growing a buffer in between would free memory a captured graph replays into
+        n_rows = int(torch.as_tensor(packed_seqlens).sum())
+        self.language_model.model.reserve(nbmax * n_rows, nbmax * int(torch.as_tensor(packed_text_indexes).numel()))
         st = self._flow_state(packed_init_noises, packed_seqlens, packed_vae_token_indexes, packed_text_indexes,
                               packed_vae_position_ids, packed_text_ids, nbmax)
         st["t_emb"] = self.time_embedder(ts.to(dev))  # every timestep of the run at once: [num_timesteps-1, H]
@@ -652,9 +684,18 @@ class Bagel:
                       cfg_text_key_values_lens=None, cfg_text_past_key_values=None,
                       cfg_text_packed_key_value_indexes=None, cfg_img_scale=1.0, cfg_img_packed_position_ids=None,
                       cfg_img_packed_query_indexes=None, cfg_img_key_values_lens=None, cfg_img_past_key_values=None,
-                      cfg_img_packed_key_value_indexes=None, cfg_type="parallel", **_taylorseer_unused):
+                      cfg_img_packed_key_value_indexes=None, cfg_type="parallel", model_pred_cache_dic=None,
+                      model_pred_current=None, model_pred_text_cache_dic=None, model_pred_text_current=None,
+                      model_pred_img_cache_dic=None, model_pred_img_current=None):
         """One velocity evaluation v_t [M, C] bf16 (reference :757-907). Implemented as a single Euler step of
         the fused path on x = 0 with dt = -1, which returns exactly the CFG-combined velocity."""
+        if any(a is not None for a in (model_pred_cache_dic, model_pred_current, model_pred_text_cache_dic,
+                                       model_pred_text_current, model_pred_img_cache_dic, model_pred_img_current)):
+            # the reference threads its TaylorSeer caches through _forward_flow (:770-775); here the step cache belongs to
+            # the planned run (FlowRunner) — a single stateless evaluation cannot honour it, so refuse instead of
+            # silently computing a full step
+            raise NotImplementedError("TaylorSeer caches are not accepted by _forward_flow; use "
+                                      "generate_image(..., enable_taylorseer=True)")
         dev = self.device
         lm = self.language_model.model
         t = torch.as_tensor(timestep).to("cpu", torch.float32).reshape(-1)
@@ -709,6 +750,7 @@ class FlowRunner:
         flops_step = 2.0 * nbmax * st["n"] * lcfg.num_hidden_layers * Hd * (qkv_o + 3 * Id)
         self.use_cuda_graph = bool(getattr(model, "use_cuda_graph", True)) and flops_step / 1.0e15 < 0.05
         self._graphs: Dict[str, Any] = {}
+        self._graph_gen: Dict[str, int] = {}
         self._eager_done: Dict[str, int] = {}
         # TaylorSeer (reference bagel.py:680-684): one schedule per branch; factor planes of the last decoder
         # layer's output for every packed row of every branch, [7 orders, nbmax*n, H] bf16
@@ -766,16 +808,22 @@ class FlowRunner:
                       self.dt_cur)
 
     def _launch(self, key: str):
+        lm = self.model.language_model.model
         g = self._graphs.get(key)
         if g is not None:
-            g.replay()
-            return
+            if self._graph_gen.get(key) == lm._ws_gen:
+                g.replay()
+                return
+            # some LM workspace was re-allocated since the capture (another, larger forward ran between two steps):
+            # the graph holds pointers into freed buffers -> drop it and capture again on the current ones
+            del self._graphs[key]
         if self.use_cuda_graph and self._eager_done.get(key, 0) >= 1:
             try:  # everything is warm (workspaces allocated, kernel attributes set): capture this step
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     self._body(key)
                 self._graphs[key] = graph
+                self._graph_gen[key] = lm._ws_gen
                 graph.replay()          # capture does not execute the work
                 return
             except Exception as e:  # capture is an optimisation; the eager launch sequence is the same work

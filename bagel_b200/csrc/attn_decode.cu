@@ -316,7 +316,7 @@ int attn_decode(const void* q, const void* k, const void* v, void* out, const in
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   // Two CTAs (8 warps, 8 cp.async rings) fit an SM: aim for one wave of ~2 CTAs per SM, at least 64 keys per CTA,
   // cluster size <= 8 (power of two: odd cluster sizes place badly, see gemm_skinny.cu).
-  static const int env_split = [] { const char* e = getenv("BAGEL_DECODE_SPLIT"); return e ? atoi(e) : 0; }();
+  static const int env_split = [] { const char* e = getenv("BAGEL_DECODE_SPLIT"); const int v = e ? atoi(e) : 0; return v > 8 ? 8 : v; }();
   const long long pairs = (long long)batch * Hk;
   int split = 1;
   while (split < 8 && pairs * split * 2 <= 2LL * sm_count()) split *= 2;

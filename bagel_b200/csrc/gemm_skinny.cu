@@ -292,7 +292,8 @@ int gemm_skinny(const void* A, long long lda, const void* W, long long ldw, void
   const int sms = sm_count();
 
   // split-K (cluster size): fill the GPU when there are fewer W slabs than SMs
-  static const int env_split = [] { const char* e = getenv("BAGEL_SKINNY_SPLIT"); return e ? atoi(e) : 0; }();
+  // portable cluster sizes only (<= 8): larger ones need cudaFuncAttributeNonPortableClusterSizeAllowed and fail at launch
+  static const int env_split = [] { const char* e = getenv("BAGEL_SKINNY_SPLIT"); const int v = e ? atoi(e) : 0; return v > 8 ? 8 : v; }();
   static const int env_stages = [] { const char* e = getenv("BAGEL_SKINNY_STAGES"); return e ? atoi(e) : 0; }();
   // Measured on B200 at B=32 (profiles/r01_skinny_gemm_split_stage_sweep.txt): what matters is (a) >= ~12 K blocks
   // per CTA, (b) about 1.5 CTAs per SM in total and (c) SMALL shared memory per CTA — a cluster whose CTAs each need a

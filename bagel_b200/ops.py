@@ -38,7 +38,14 @@ def kernel_timer_stop():
     return [a.elapsed_time(b) for a, b in ev]
 
 
+def _opt(t: Optional[torch.Tensor], dtype, name: str) -> None:
+    if t is not None:
+        _req(t, dtype, name)
+
+
 def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not torch.is_tensor(t):
+        raise _cabi.BagelB200Error(f"{name}: expected a tensor, got {type(t).__name__}")
     if not t.is_cuda:
         raise _cabi.BagelB200Error(f"{name}: expected a CUDA tensor (bagel_b200 has no CPU path)")
     if t.dtype != dtype:
@@ -99,14 +106,38 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 def gemm_qkv_norm_rope(a, w, bias, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk,
                        eps: float, fp32_flow: bool, row_map=None):
     """Fused QKV projection + per-head q/k RMSNorm + RoPE + bf16 cast + K/V placement (head_dim 128)."""
-    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w"); _req(bias, torch.bfloat16, "bias")
     M, K = a.shape
     assert w.shape == ((Hq + 2 * Hk) * 128, K)
+    _qkv_tail_checks(M if row_map is None else None, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows,
+                     Hq, Hk, 128)
+    _opt(row_map, torch.int32, "row_map")
     rc = _cabi.lib().bagel_gemm_qkv_norm_rope(
         _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), M, K, _ptr(row_map), _ptr(q_w0), _ptr(k_w0),
         _ptr(q_w1), _ptr(k_w1), _ptr(expert), _ptr(cos), _ptr(sin), _ptr(q_out), q_out.stride(0), _ptr(k_out),
         _ptr(v_out), k_out.stride(0), _ptr(kv_rows), Hq, Hk, float(eps), int(fp32_flow), _stream())
     _cabi.check(rc, "bagel_gemm_qkv_norm_rope")
+
+
+def _qkv_tail_checks(n_rows, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D):
+    """Shared argument checks of the two q/k-norm + RoPE + KV-placement entry points (raw pointers cross the C ABI)."""
+    for t, nm in ((q_w0, "q_w0"), (k_w0, "k_w0")):
+        _req(t, torch.bfloat16, nm)
+        assert t.numel() == D, f"{nm}: expected {D} elements"
+    _opt(q_w1, torch.bfloat16, "q_w1"); _opt(k_w1, torch.bfloat16, "k_w1")
+    _opt(expert, torch.uint8, "expert")
+    _req(cos, torch.float32, "cos"); _req(sin, torch.float32, "sin")
+    assert cos.shape == sin.shape and cos.shape[-1] == D // 2 and cos.is_contiguous() and sin.is_contiguous()
+    _req(q_out, torch.bfloat16, "q_out"); _req(k_out, torch.bfloat16, "k_out"); _req(v_out, torch.bfloat16, "v_out")
+    assert q_out.shape[-1] >= Hq * D and k_out.shape[-1] >= Hk * D and v_out.shape[-1] >= Hk * D
+    assert k_out.stride(0) == v_out.stride(0), "K and V buffers must share their row stride"
+    _opt(kv_rows, torch.int32, "kv_rows")
+    if n_rows is not None:
+        assert cos.shape[0] >= n_rows and q_out.shape[0] >= n_rows
+        if kv_rows is not None:
+            assert kv_rows.numel() >= n_rows
+        if expert is not None:
+            assert expert.numel() >= n_rows
 
 
 def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,
@@ -169,6 +200,9 @@ def rope_table(pos: torch.Tensor, inv_freq: torch.Tensor, round_bf16: bool = Tru
 
 def rope_table_into(pos: torch.Tensor, inv_freq: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, round_bf16: bool = True):
     """rope_table writing into caller-owned buffers (graph-replayable decode step)."""
+    _req(pos, torch.int64, "pos"); _req(inv_freq, torch.float32, "inv_freq")
+    _req(cos, torch.float32, "cos"); _req(sin, torch.float32, "sin")
+    assert cos.is_contiguous() and sin.is_contiguous() and cos.numel() >= pos.numel() * inv_freq.numel() <= sin.numel()
     rc = _cabi.lib().bagel_rope_table(_ptr(pos), _ptr(inv_freq), _ptr(cos), _ptr(sin), pos.numel(), inv_freq.numel(),
                                       int(round_bf16), _stream())
     _cabi.check(rc, "bagel_rope_table")
@@ -178,6 +212,8 @@ def qk_norm_rope(qkv, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_
                  eps: float, fp32_flow: bool):
     _req(qkv, torch.bfloat16, "qkv")
     N = qkv.shape[0]
+    assert qkv.shape[1] >= (Hq + 2 * Hk) * D
+    _qkv_tail_checks(N, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D)
     rc = _cabi.lib().bagel_qk_norm_rope(_ptr(qkv), qkv.stride(0), _ptr(q_w0), _ptr(k_w0), _ptr(q_w1), _ptr(k_w1),
                                         _ptr(expert), _ptr(cos), _ptr(sin), _ptr(q_out), q_out.stride(0), _ptr(k_out),
                                         _ptr(v_out), k_out.stride(0), _ptr(kv_rows), N, Hq, Hk, D, float(eps),
@@ -190,6 +226,13 @@ def copy_rows(src, dst, src_rows=None, dst_rows=None, M: Optional[int] = None):
     if M is None:
         M = src_rows.numel() if src_rows is not None else (dst_rows.numel() if dst_rows is not None else src.shape[0])
     H = src.shape[-1]
+    _opt(src_rows, torch.int32, "src_rows"); _opt(dst_rows, torch.int32, "dst_rows")
+    if dst.shape[-1] < H:
+        raise _cabi.BagelB200Error(f"copy_rows: dst rows are {dst.shape[-1]} wide, src rows {H}")
+    if src_rows is not None and src_rows.numel() < M or dst_rows is not None and dst_rows.numel() < M:
+        raise _cabi.BagelB200Error("copy_rows: index tensor shorter than M")
+    if src_rows is None and src.shape[0] < M or dst_rows is None and dst.shape[0] < M:
+        raise _cabi.BagelB200Error("copy_rows: M exceeds the rows of an un-indexed operand")
     rc = _cabi.lib().bagel_copy_rows_bf16(_ptr(src), src.stride(0), _ptr(src_rows), _ptr(dst), dst.stride(0),
                                           _ptr(dst_rows), M, H, _stream())
     _cabi.check(rc, "bagel_copy_rows_bf16")
@@ -199,7 +242,11 @@ def copy_rows(src, dst, src_rows=None, dst_rows=None, M: Optional[int] = None):
 def latent_embed_add(proj, t_emb, pos_table, pos_ids, seq, dst_rows):
     """seq[dst_rows[i]] = bf16(bf16(proj[i] + t_emb) + pos_table[pos_ids[i]]); t_emb / dst_rows may be None."""
     M, H = proj.shape
-    _req(pos_ids, torch.int64, "pos_ids")
+    _req(proj, torch.bfloat16, "proj"); _opt(t_emb, torch.bfloat16, "t_emb"); _req(pos_table, torch.bfloat16, "pos_table")
+    _req(pos_ids, torch.int64, "pos_ids"); _req(seq, torch.bfloat16, "seq"); _opt(dst_rows, torch.int32, "dst_rows")
+    assert pos_table.shape[-1] == H and seq.shape[-1] >= H and pos_ids.numel() >= M
+    assert t_emb is None or t_emb.numel() >= H
+    assert (dst_rows.numel() >= M) if dst_rows is not None else (seq.shape[0] >= M)
     rc = _cabi.lib().bagel_latent_embed_add(_ptr(proj), proj.stride(0), _ptr(t_emb), _ptr(pos_table), pos_table.stride(0),
                                             _ptr(pos_ids), _ptr(seq), seq.stride(0), _ptr(dst_rows), M, H, _stream())
     _cabi.check(rc, "bagel_latent_embed_add")
@@ -212,6 +259,12 @@ def cfg_euler_step(v, v_text, v_img, rows, x, norms_ws, cfg_text_scale, cfg_img_
                    dt_dev: Optional[torch.Tensor] = None):
     _req(x, torch.float32, "x")
     M, Cc = x.shape
+    assert x.is_contiguous()
+    _req(v, torch.bfloat16, "v"); _opt(v_text, torch.bfloat16, "v_text"); _opt(v_img, torch.bfloat16, "v_img")
+    _req(rows, torch.int32, "rows"); _req(norms_ws, torch.float32, "norms_ws"); _opt(dt_dev, torch.float32, "dt_dev")
+    assert rows.numel() >= M and norms_ws.numel() >= 2 and v.shape[-1] >= Cc
+    for t in (v_text, v_img):
+        assert t is None or t.stride(0) == v.stride(0), "CFG branches must share the row stride of v"
     rc = _cabi.lib().bagel_cfg_euler_step(_ptr(v), _ptr(v_text), _ptr(v_img), v.stride(0), _ptr(rows), _ptr(x),
                                           _ptr(norms_ws), M, Cc, float(cfg_text_scale), float(cfg_img_scale),
                                           float(renorm_min), RENORM[renorm_type], float(dt), _ptr(dt_dev), _stream())
@@ -310,6 +363,9 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
 # text decode bookkeeping (device-resident)
 # ---------------------------------------------------------------------------------------------------------
 def decode_prepare(k_begin, seq_len, kv_rows, seqused):
+    for t, nm in ((k_begin, "k_begin"), (seq_len, "seq_len"), (kv_rows, "kv_rows"), (seqused, "seqused")):
+        _req(t, torch.int32, nm)
+    assert k_begin.numel() >= seq_len.numel() + 1 and kv_rows.numel() >= seq_len.numel() <= seqused.numel()
     rc = _cabi.lib().bagel_decode_prepare(_ptr(k_begin), _ptr(seq_len), _ptr(kv_rows), _ptr(seqused), seq_len.numel(), _stream())
     _cabi.check(rc, "bagel_decode_prepare")
 
@@ -322,6 +378,9 @@ def argmax_rows(logits: torch.Tensor, tokens: torch.Tensor, tokens32: Optional[t
 
 
 def decode_advance(seq_len, pos, tokens, history, step_dev):
+    _req(seq_len, torch.int32, "seq_len"); _req(pos, torch.int64, "pos"); _req(tokens, torch.int64, "tokens")
+    _req(history, torch.int64, "history"); _req(step_dev, torch.int32, "step_dev")
+    assert pos.numel() == seq_len.numel() == tokens.numel() and history.is_contiguous() and history.shape[-1] == seq_len.numel()
     rc = _cabi.lib().bagel_decode_advance(_ptr(seq_len), _ptr(pos), _ptr(tokens), _ptr(history), _ptr(step_dev),
                                           seq_len.numel(), _stream())
     _cabi.check(rc, "bagel_decode_advance")

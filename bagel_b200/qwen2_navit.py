@@ -150,6 +150,7 @@ class Qwen2Model:
         # same expression as the reference's default rope init (fp32), computed on the host then moved
         self.inv_freq = (1.0 / (config.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(self.device)
         self._ws: Dict[str, torch.Tensor] = {}
+        self._ws_gen = 0   # bumped on every workspace (re)allocation: CUDA graphs captured over older buffers are stale
 
     # ----------------------------------------------------------------------------------------------
     def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
@@ -158,7 +159,21 @@ class Qwen2Model:
         if t is None or t.shape[0] < rows or t.shape[1] != cols:
             t = torch.empty((rows, cols), dtype=BF16, device=self.device)
             self._ws[name] = t
+            self._ws_gen += 1
         return t[:rows]
+
+    def reserve(self, rows: int, text_rows: int = 0) -> None:
+        """Size every run_layers()/final_norm() workspace for `rows` packed tokens (and `text_rows` und-expert rows) up
+        front, so a later, larger call cannot replace a buffer that a captured CUDA graph still points into."""
+        cfg = self.config
+        H, D, I = cfg.hidden_size, cfg.head_dim, cfg.intermediate_size
+        Hq, Hk = cfg.num_attention_heads, cfg.num_key_value_heads
+        for name, cols in (("xa", H), ("xb", H), ("h", H), ("out", H), ("qkv", (Hq + 2 * Hk) * D), ("q", Hq * D),
+                           ("att", Hq * D), ("act", I)):
+            self._buf(name, rows, cols)
+        if text_rows:
+            for name, cols in (("h_text", H), ("att_text", Hq * D), ("act_text", I)):
+                self._buf(name, text_rows, cols)
 
     def make_plan(self, **kw) -> ForwardPlan:
         return ForwardPlan(self, **kw)
@@ -270,7 +285,8 @@ class Qwen2Model:
                           packed_key_value_indexes=None, update_past_key_values=True, is_causal=True, mode="und",
                           packed_vae_token_indexes=None, packed_text_indexes=None) -> BaseNavitOutputWithPast:
         if self.enable_taylorseer:
-            raise NotImplementedError("TaylorSeer step caching is out of scope (SURVEY.md §8f #1)")
+            raise NotImplementedError("the TaylorSeer step cache lives in the planned sampler: call "
+                                      "Bagel.generate_image(enable_taylorseer=True) (bagel_b200/bagel.py FlowRunner)")
         if not self.use_moe:
             mode = "und"
         has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None

@@ -59,7 +59,7 @@ def sincos_2d_table(embed_dim, grid_size):
 def timestep_embedding(t, dim=256, max_period=10000):
     """modeling_utils.py:87-105"""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -77,7 +77,8 @@ def flattened_position_ids(img_h, img_w, patch, max_side):
 
 
 def lm_sub(sd):
-    return {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+    out = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+    return out if type(sd) is dict else type(sd)(out)      # keeps om.LazyF32 lazy
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -227,7 +228,7 @@ def forward_flow(sd, fc: FlowConfig, x_t, timestep, packed_vae_token_indexes, pa
 def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_timesteps=24, timestep_shift=1.0,
                    cfg_renorm_min=0.0, cfg_renorm_type="global", cfg_interval=(0, 1), cfg_text_scale=1.0,
                    cfg_text=None, cfg_img_scale=1.0, cfg_img=None, trace: Optional[list] = None,
-                   enable_taylorseer: bool = False):
+                   enable_taylorseer: bool = False, x_trace: Optional[list] = None, max_steps: Optional[int] = None):
     """bagel.py:644-754. gen_input = prepare_vae_latent(...) dict. Returns the tuple of per-sample latents.
     enable_taylorseer: one TaylorSeer cache per branch, created per call (bagel.py:680-684)."""
     x_t = gen_input["packed_init_noises"]
@@ -239,7 +240,9 @@ def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_tim
     dts = ts[:-1] - ts[1:]
     ts = ts[:-1]
     for i, t in enumerate(ts):
-        timestep = torch.tensor([t] * x_t.shape[0])
+        if max_steps is not None and i >= max_steps:
+            break
+        timestep = torch.tensor([t] * x_t.shape[0]).to(x_t.device)
         on = bool(t > cfg_interval[0] and t <= cfg_interval[1])
         v = forward_flow(sd, fc, x_t, timestep, gen_input["packed_vae_token_indexes"],
                          gen_input["packed_vae_position_ids"], gen_input["packed_text_ids"],
@@ -249,7 +252,9 @@ def generate_image(sd, fc: FlowConfig, gen_input: Dict, past_key_values, num_tim
                          cfg_text_scale if on else 1.0, cfg_text, cfg_img_scale if on else 1.0, cfg_img, taylor=taylor)
         if trace is not None:
             trace.append(v.clone())
-        x_t = x_t - v * dts[i]
+        x_t = x_t - v * dts[i].to(x_t.device)
+        if x_trace is not None:
+            x_trace.append(x_t.clone())
     return x_t.split((gen_input["packed_seqlens"] - 2).tolist())
 
 

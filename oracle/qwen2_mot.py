@@ -16,6 +16,24 @@ import torch.nn.functional as F
 
 BF16 = torch.bfloat16
 _AUTOCAST = [torch.bfloat16]  # dtype nn.Linear / attention run in; see high_precision()
+# Optional replacement for the attention contraction: callable (q, k, v, q_lens, k_lens, causal) -> out, or None for
+# the restatement below (which is what is pinned bit-for-bit against the reference's CPU run). oracle/gpu_leg.py
+# installs the real flash_attn_varlen_func here to form the "reference PyTorch path on the GPU" leg.
+_ATTN_IMPL = [None]
+
+
+class attention_impl:
+    """Context manager: run the oracle with another varlen attention (e.g. flash-attn on CUDA)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __enter__(self):
+        self.prev = _ATTN_IMPL[0]
+        _ATTN_IMPL[0] = self.fn
+
+    def __exit__(self, *a):
+        _ATTN_IMPL[0] = self.prev
 
 
 class high_precision:
@@ -28,6 +46,14 @@ class high_precision:
 
     def __exit__(self, *a):
         _AUTOCAST[0] = torch.bfloat16
+
+
+class LazyF32(dict):
+    """State dict whose values are upcast to fp32 on access: the fp32-truth evaluation of a 7B model without holding a
+    second, 57 GB fp32 copy of the weights (use together with high_precision())."""
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self, k).float()
 
 
 @dataclass
@@ -63,7 +89,7 @@ def rms_norm(x, w, eps):
 
 def rope_tables(position_ids, head_dim, theta, dtype):
     """modeling_qwen2.py:130-150 — fp32 angles, halves duplicated, then cast to the hidden-stream dtype."""
-    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    inv_freq = (1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))).to(position_ids.device)
     freqs = (inv_freq[None, :, None].float() @ position_ids[None, None, :].float()).transpose(1, 2)[0]
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
@@ -90,6 +116,8 @@ def swiglu_mlp(x, sd, pfx):
 def varlen_attention(q, k, v, q_lens, k_lens, causal):
     """Semantics of flash_attn_varlen_func as the reference calls it (qwen2_navit.py:579-588): per-sample
     softmax(q k^T / sqrt(d)) v, GQA, bottom-right aligned causal mask, fp32 math on bf16 inputs, bf16 out."""
+    if _ATTN_IMPL[0] is not None and _AUTOCAST[0] == torch.bfloat16:
+        return _ATTN_IMPL[0](q, k, v, q_lens, k_lens, causal)
     out = torch.empty_like(q)
     rep = q.shape[1] // k.shape[1]
     scale = q.shape[-1] ** -0.5
@@ -102,7 +130,7 @@ def varlen_attention(q, k, v, q_lens, k_lens, causal):
             vb = v[ks:ks + lk].float().transpose(0, 1).repeat_interleave(rep, dim=0)
             s = torch.matmul(qb, kb.transpose(1, 2)) * scale
             if causal:
-                keep = torch.ones(lq, lk, dtype=torch.bool).tril(diagonal=lk - lq)
+                keep = torch.ones(lq, lk, dtype=torch.bool, device=q.device).tril(diagonal=lk - lq)
                 s = s.masked_fill(~keep, float("-inf"))
             out[qs:qs + lq] = torch.matmul(torch.softmax(s, dim=-1), vb).transpose(0, 1).to(q.dtype)
         qs += lq
