@@ -49,6 +49,7 @@ SIGNATURES = {
     "bagel_transpose_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     "bagel_taylor_update_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
     "bagel_taylor_eval_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _i, _vp]),
+    "bagel_siglip_rope2d_bf16": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -676,6 +676,32 @@ class Bagel:
                 break
         return history[:steps].clone()
 
+    # ------------------------------------------------------------------------------------------
+    # evaluation entry point: images + prompt -> text (reference bagel.py:1004-1075)
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def chat(self, tokenizer, new_token_ids, image_transform, images, prompt, max_length: int,
+             do_sample: bool = False, temperature: float = 1.0):
+        """Same call order as the reference: one SigLIP prefill per image (prepare_vit_images ->
+        forward_cache_update_vit), then the prompt (prepare_prompts -> forward_cache_update_text), then greedy / sampled
+        decode from <|im_start|> until <|im_end|>; returns the decoded answer between the two markers."""
+        past_key_values = NaiveCache(self.config.llm_config.num_hidden_layers)
+        newlens, new_rope = [0], [0]
+        for image in images:
+            generation_input, newlens, new_rope = self.prepare_vit_images(
+                curr_kvlens=newlens, curr_rope=new_rope, images=[image], transforms=image_transform,
+                new_token_ids=new_token_ids)
+            past_key_values = self.forward_cache_update_vit(past_key_values, **generation_input)
+        generation_input, newlens, new_rope = self.prepare_prompts(
+            curr_kvlens=newlens, curr_rope=new_rope, prompts=[prompt], tokenizer=tokenizer, new_token_ids=new_token_ids)
+        past_key_values = self.forward_cache_update_text(past_key_values, **generation_input)
+        generation_input = self.prepare_start_tokens(newlens, new_rope, new_token_ids)
+        unpacked_latent = self.generate_text(
+            past_key_values=past_key_values, max_length=max_length, do_sample=do_sample, temperature=temperature,
+            end_token_id=new_token_ids["eos_token_id"], **generation_input)
+        output = tokenizer.decode(unpacked_latent[:, 0])
+        return output.split("<|im_end|>")[0].split("<|im_start|>")[1]
+
     @torch.no_grad()
     def _forward_flow(self, x_t, timestep, packed_vae_token_indexes, packed_vae_position_ids, packed_text_ids,
                       packed_text_indexes, packed_indexes, packed_position_ids, packed_seqlens, key_values_lens,

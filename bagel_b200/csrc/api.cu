@@ -104,5 +104,5 @@ int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int
 }  // namespace bagel
 
 extern "C" const char* bagel_last_error(void) { return bagel::g_err; }
-extern "C" int bagel_abi_version(void) { return 2; }
+extern "C" int bagel_abi_version(void) { return 3; }
 extern "C" long long bagel_launch_count(void) { return bagel::g_launches.load(); }

@@ -157,14 +157,18 @@ __global__ void rope_table_kernel(const long long* __restrict__ pos, const float
 // (PackedAttentionMoT.forward_inference, qwen2_navit.py:518-519 / 542-557 and the KV merge :559-574).
 //   qkv   [N, (Hq+2Hk)*D]  bf16 output of the fused QKV projection (bias included)
 //   q_out [N, Hq*D]; k_out/v_out [rows, Hk*D] written at row kv_rows[r] (the reference's packed_query_indexes)
-// fp32_flow = 1 reproduces mode="gen" (fp32 norm + RoPE, one final bf16 cast); 0 reproduces mode="und"
-// (every op rounds to bf16). One warp per (row, head).
+// `flow` selects the reference's rounding points (SURVEY.md 8a dtype table):
+//   0  mode A (bf16 weights), und / dense attention: every op rounds to bf16, bf16-rounded cos/sin
+//   1  mode A, MoT gen branch: fp32 norm + RoPE (bf16 norm weights, bf16-rounded cos/sin), one final bf16 cast
+//   2  mode B (fp32 weights), und / dense: bf16(x * r) * w_fp32 -> fp32, RoPE in fp32 with fp32 cos/sin
+//   3  mode B, MoT gen branch: everything fp32 (fp32 norm weights, fp32 cos/sin)
+// flows 2 and 3 read the norm weights as fp32. One warp per (row, head).
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128)
-qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, const __nv_bfloat16* __restrict__ qw0,
-                    const __nv_bfloat16* __restrict__ kw0, const __nv_bfloat16* __restrict__ qw1,
-                    const __nv_bfloat16* __restrict__ kw1, const uint8_t* __restrict__ expert,
+qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, const void* __restrict__ qw0,
+                    const void* __restrict__ kw0, const void* __restrict__ qw1,
+                    const void* __restrict__ kw1, const uint8_t* __restrict__ expert,
                     const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                     __nv_bfloat16* __restrict__ q_out, long long ld_q, __nv_bfloat16* __restrict__ k_out,
                     __nv_bfloat16* __restrict__ v_out, long long ld_kv, const int* __restrict__ kv_rows, int N,
@@ -206,7 +210,7 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, con
       }
       continue;
     }
-    const __nv_bfloat16* w = (hh < Hq) ? (gen ? qw1 : qw0) : (gen ? kw1 : kw0);
+    const void* w = (hh < Hq) ? (gen ? qw1 : qw0) : (gen ? kw1 : kw0);
     float ss = 0.f;
 #pragma unroll
     for (int t = 0; t < E; ++t) ss += a[t] * a[t] + b[t] * b[t];
@@ -214,12 +218,16 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, con
     const float r = rsqrtf(ss / (float)D + eps);
 #pragma unroll
     for (int t = 0; t < E; ++t) {
-      const float wa = __bfloat162float(w[lane * E + t]);
-      const float wb = __bfloat162float(w[HALF + lane * E + t]);
+      const float wa = fp32_flow >= 2 ? static_cast<const float*>(w)[lane * E + t]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[lane * E + t]);
+      const float wb = fp32_flow >= 2 ? static_cast<const float*>(w)[HALF + lane * E + t]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[HALF + lane * E + t]);
       float ya, yb, oa, ob;
       if (fp32_flow) {
-        ya = __fmul_rn(wa, __fmul_rn(a[t], r));
-        yb = __fmul_rn(wb, __fmul_rn(b[t], r));
+        const float na = (fp32_flow == 2) ? bf16_round(a[t] * r) : __fmul_rn(a[t], r);   // flow 2: q_norm runs on bf16 q
+        const float nb = (fp32_flow == 2) ? bf16_round(b[t] * r) : __fmul_rn(b[t], r);
+        ya = __fmul_rn(wa, na);
+        yb = __fmul_rn(wb, nb);
         // q*cos + rotate_half(q)*sin, each product rounded separately (torch does not fuse)
         oa = __fadd_rn(__fmul_rn(ya, cs[t]), __fmul_rn(-yb, sn[t]));
         ob = __fadd_rn(__fmul_rn(yb, cs[t]), __fmul_rn(ya, sn[t]));
@@ -629,12 +637,11 @@ extern "C" int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void*
   if (N <= 0) return 0;
   if (D != 64 && D != 128) return set_error(BAGEL_ERR_SHAPE, "bagel_qk_norm_rope: head_dim must be 64 or 128");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (fp32_flow < 0 || fp32_flow > 3) return set_error(BAGEL_ERR_ARG, "bagel_qk_norm_rope: flow must be 0..3");
 #define QK_ARGS                                                                                                   \
-  static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(q_w0),                        \
-      static_cast<const __nv_bfloat16*>(k_w0), static_cast<const __nv_bfloat16*>(q_w1),                           \
-      static_cast<const __nv_bfloat16*>(k_w1), expert, cos_t, sin_t, static_cast<__nv_bfloat16*>(q_out), ld_q,    \
-      static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), ld_kv, kv_rows, N, Hq, Hk, eps,     \
-      fp32_flow
+  static_cast<const __nv_bfloat16*>(qkv), ld_qkv, q_w0, k_w0, q_w1, k_w1, expert, cos_t, sin_t,                   \
+      static_cast<__nv_bfloat16*>(q_out), ld_q, static_cast<__nv_bfloat16*>(k_out),                               \
+      static_cast<__nv_bfloat16*>(v_out), ld_kv, kv_rows, N, Hq, Hk, eps, fp32_flow
   if (D == 128) qk_norm_rope_kernel<128><<<N, 128, 0, s>>>(QK_ARGS);
   else qk_norm_rope_kernel<64><<<N, 128, 0, s>>>(QK_ARGS);
 #undef QK_ARGS
@@ -774,6 +781,142 @@ extern "C" int bagel_taylor_eval_bf16(const void* factors, long long plane_strid
   taylor_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(factors), plane_stride, n_factors, k, static_cast<__nv_bfloat16*>(out), ldo, rows,
       H / 8);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SigLIP 2-D RoPE (modeling/bagel/siglip_navit.py:102-142, 224-230): the first half of every q/k head is rotated by the
+// ROW table, the second half by the COLUMN table of the patch position (RotaryEmbedding2D buffers, fp32), in place on
+// the q and k heads of the fused QKV buffer. The reference computes q*cos + rotate_half(q)*sin with bf16 q and fp32
+// tables => fp32 products and sum (each rounded separately), one final cast to bf16.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace bagel {
+__global__ void siglip_rope2d_kernel(__nv_bfloat16* __restrict__ x, long long ld, int n, int heads, int head_stride, int d,
+                                     const long long* __restrict__ pos, const float* __restrict__ cos_h,
+                                     const float* __restrict__ sin_h, const float* __restrict__ cos_w,
+                                     const float* __restrict__ sin_w) {
+  const int half = d / 2, quarter = d / 4;
+  const long long total = (long long)n * heads * 2 * quarter;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % quarter);
+  long long t = idx / quarter;
+  const int hw = (int)(t & 1);
+  t >>= 1;
+  const int head = (int)(t % heads);
+  const long long tok = t / heads;
+  __nv_bfloat16* p = x + tok * ld + (long long)head * head_stride + hw * half;
+  const long long row = pos[tok] * half;
+  const float* ct = (hw ? cos_w : cos_h) + row;
+  const float* st = (hw ? sin_w : sin_h) + row;
+  const float a = __bfloat162float(p[j]), b = __bfloat162float(p[j + quarter]);
+  const float oa = __fadd_rn(__fmul_rn(a, ct[j]), __fmul_rn(-b, st[j]));
+  const float ob = __fadd_rn(__fmul_rn(b, ct[j + quarter]), __fmul_rn(a, st[j + quarter]));
+  p[j] = __float2bfloat16_rn(oa);
+  p[j + quarter] = __float2bfloat16_rn(ob);
+}
+}  // namespace bagel
+
+extern "C" int bagel_siglip_rope2d_bf16(void* x, long long ld, int n_tokens, int heads, int head_stride, int head_dim,
+                                        const long long* pos_ids, const float* cos_h, const float* sin_h,
+                                        const float* cos_w, const float* sin_w, void* stream) {
+  if (n_tokens <= 0 || heads <= 0) return 0;
+  if (head_dim <= 0 || (head_dim % 4) || head_stride < head_dim)
+    return bagel::set_error(BAGEL_ERR_SHAPE, "bagel_siglip_rope2d_bf16: head_dim must be a positive multiple of 4 and <= head_stride");
+  if (!x || !pos_ids || !cos_h || !sin_h || !cos_w || !sin_w)
+    return bagel::set_error(BAGEL_ERR_ARG, "bagel_siglip_rope2d_bf16: null pointer");
+  const long long total = (long long)n_tokens * heads * (head_dim / 2);
+  bagel::siglip_rope2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), ld, n_tokens, heads, head_stride, head_dim, pos_ids, cos_h, sin_h, cos_w, sin_w);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dtype mode B (fp32 master weights under autocast: eval/gen/gen_images_mp.py:159-175 + :73; SURVEY.md 8a dtype table):
+// the residual stream and the norm outputs are fp32, every nn.Linear still runs bf16 x bf16 -> bf16.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace bagel {
+
+// Qwen2RMSNorm on an fp32 row with fp32 weights: y = w * (x * rsqrt(mean(x^2) + eps)), both products rounded to fp32
+// (modeling_qwen2.py:54-59 with input_dtype = fp32). OUT = float keeps that value (final norm returned to the caller);
+// OUT = bf16 adds the autocast cast in front of the next nn.Linear. Block per row, second pass re-reads x from L1/L2.
+template <typename OUT>
+__global__ void __launch_bounds__(256)
+rmsnorm_f32_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w0, const float* __restrict__ w1,
+                   const uint8_t* __restrict__ expert, OUT* __restrict__ y, long long ldy, int H, float eps) {
+  const long long row = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int nvec = H >> 2;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const float4 v = xr[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sh[i];
+  const float r = rsqrtf(tot / (float)H + eps);
+  const float* w = (expert != nullptr && w1 != nullptr && expert[row]) ? w1 : w0;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const float4 v = xr[i], ww = wr[i];
+    const float o0 = __fmul_rn(ww.x, __fmul_rn(v.x, r)), o1 = __fmul_rn(ww.y, __fmul_rn(v.y, r));
+    const float o2 = __fmul_rn(ww.z, __fmul_rn(v.z, r)), o3 = __fmul_rn(ww.w, __fmul_rn(v.w, r));
+    if constexpr (sizeof(OUT) == 4) {
+      reinterpret_cast<float4*>(y + row * ldy)[i] = make_float4(o0, o1, o2, o3);
+    } else {
+      reinterpret_cast<uint2*>(y + row * ldy)[i] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
+// latent-in tail with an fp32 hidden stream (mode B): seq32[dst] = fp32( bf16(proj + t_emb) + pos_table_fp32[pos] ).
+__global__ void __launch_bounds__(128)
+latent_embed_add_f32_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, const __nv_bfloat16* __restrict__ t_emb,
+                            const float* __restrict__ pos_table, long long ldt, const long long* __restrict__ pos_ids,
+                            float* __restrict__ seq, long long lds, const int* __restrict__ dst_rows, int M, int H) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const __nv_bfloat16* pr = proj + (long long)i * ldp;
+  const float* pt = pos_table + pos_ids[i] * ldt;
+  float* d = seq + (long long)(dst_rows ? dst_rows[i] : i) * lds;
+  for (int c = lane; c < H; c += 32) {
+    const float a = __bfloat162float(pr[c]);
+    const float s = t_emb ? bf16_round(a + __bfloat162float(t_emb[c])) : a;
+    d[c] = __fadd_rn(s, pt[c]);
+  }
+}
+}  // namespace bagel
+
+extern "C" int bagel_rmsnorm_f32(const float* x, long long ldx, const float* w0, const float* w1, const uint8_t* expert,
+                                 void* y, long long ldy, int out_f32, int N, int H, float eps, void* stream) {
+  if (N <= 0) return 0;
+  if ((H % 4) || (ldx % 4) || (ldy % 4)) return bagel::set_error(BAGEL_ERR_ALIGN, "bagel_rmsnorm_f32: H, ldx, ldy must be multiples of 4");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_f32) bagel::rmsnorm_f32_kernel<float><<<N, 256, 0, s>>>(x, ldx, w0, w1, expert, static_cast<float*>(y), ldy, H, eps);
+  else bagel::rmsnorm_f32_kernel<__nv_bfloat16><<<N, 256, 0, s>>>(x, ldx, w0, w1, expert, static_cast<__nv_bfloat16*>(y), ldy, H, eps);
+  COUNT_LAUNCH();
+  BAGEL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bagel_latent_embed_add_f32(const void* proj, long long ldp, const void* t_emb, const float* pos_table,
+                                          long long ldt, const long long* pos_ids, float* seq, long long lds,
+                                          const int* dst_rows, int M, int H, void* stream) {
+  if (M <= 0) return 0;
+  bagel::latent_embed_add_f32_kernel<<<(M + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(proj), ldp, static_cast<const __nv_bfloat16*>(t_emb), pos_table, ldt, pos_ids, seq,
+      lds, dst_rows, M, H);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -36,11 +36,12 @@ enum GemmEpilogue : int {
   EPI_SILU = 4,    // C = bf16(silu(bf16(acc + bias)))                  (timestep MLP)
   EPI_F32 = 5,     // C32 = acc (+ bias) as fp32                        (attention logits of the VAE mid block)
   EPI_QKV = 6,     // fused q/k RMSNorm + RoPE + bf16 cast + K/V placement  (PackedAttentionMoT, head_dim 128)
+  EPI_RESID_F32 = 7,  // C32 = resid32 + bf16(acc + bias): fp32 residual stream of dtype mode B (fp32 master weights)
 };
 
 // Extra arguments of the fused QKV epilogue (see bagel_gemm_qkv_norm_rope in include/bagel_b200.h).
 struct QkvEpi {
-  const __nv_bfloat16 *qw0, *kw0, *qw1, *kw1;  // per-head RMSNorm weights [128]: und expert / gen expert (may be null)
+  const void *qw0, *kw0, *qw1, *kw1;  // per-head RMSNorm weights [128]: und / gen expert (may be null); bf16, fp32 for flow >= 2
   const uint8_t* expert;                       // [rows] 1 = gen expert
   const float *cos_t, *sin_t;                  // [rows, 64]
   __nv_bfloat16 *q_out, *k_out, *v_out;
@@ -48,7 +49,7 @@ struct QkvEpi {
   const int* kv_rows;                          // destination row of each token in the merged K/V buffers
   int Hq, Hk;
   float eps;
-  int fp32_flow;
+  int fp32_flow;  // rounding-point flow 0..3, see qk_norm_rope_kernel in elementwise.cu
 };
 
 struct GemmParams {
@@ -57,10 +58,13 @@ struct GemmParams {
   long long ldc;
   const __nv_bfloat16* bias;   // [N] or null
   const __nv_bfloat16* resid;  // [*, ldr] or null (EPI_RESID)
+  const float* resid32;        // EPI_RESID_F32
   long long ldr;
   const int* row_map;  // optional: output (and residual) row of A-row r is row_map[r]
   int num_m, num_n, num_tiles;
   int group_m;  // rasterisation: group_m M-tiles share one sweep over the N tiles (their A panels stay in L2)
+  int group_n;  // N super-tiles: all M groups sweep group_n N-tiles before the next group_n (that W sub-panel stays in L2)
+  int hints;    // bit 0: W loads L2 evict_last, bit 1: A loads evict_first, bit 2: streaming (evict-first) output stores
   // --- implicit-GEMM convolution (CONV kernels only): A is an NHWC activation tensor [B, Hi, Wi, Cin] read through a
   // 4-D TMA map; an M tile is a th x tw patch of output pixels (th*tw = 128) of one image; K runs over
   // (tap, 64-channel chunk); output / residual rows are NHWC pixel indices.
@@ -83,14 +87,28 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
-  const int group_size = group_m * num_n;
-  const int g = tile / group_size;
+// Two-level raster. Outer: N super-tiles of group_n N-tiles (the W sub-panel of a super-tile, group_n * BN * K * 2 bytes, is
+// what should stay L2-resident while every M group sweeps it). Inner: groups of group_m M-tiles, M fastest, so the ~148
+// CTAs running at any moment cover group_m x (148 / group_m) tiles and share their A / W tiles through the L2.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int group_n, int& m_blk,
+                                            int& n_blk) {
+  const int super_size = group_n * num_m;
+  const int s = tile / super_size;
+  const int n0 = s * group_n;
+  const int nn = min(group_n, num_n - n0);
+  const int rem = tile - s * super_size;
+  const int group_size = group_m * nn;
+  const int g = rem / group_size;
   const int first_m = g * group_m;
   const int gm = min(num_m - first_m, group_m);
-  const int local = tile - g * group_size;
+  const int local = rem - g * group_size;
   m_blk = first_m + local % gm;
-  n_blk = local / gm;
+  n_blk = n0 + local / gm;
+}
+
+__device__ __forceinline__ void store16(void* dst, const uint4& v, bool streaming) {
+  if (streaming) __stcs(reinterpret_cast<uint4*>(dst), v);   // st.global.cs: evict-first, the output is not re-read by this kernel
+  else *reinterpret_cast<uint4*>(dst) = v;
 }
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -148,9 +166,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : kEvictNormal;
+      const uint64_t hint_w = (p.hints & 1) ? kEvictLast : kEvictNormal;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(tile, p.num_m, p.num_n, p.group_m, m_blk, n_blk);
+        tile_coords(tile, p.num_m, p.num_n, p.group_m, p.group_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -163,11 +183,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
             const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
             tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], cc * BK, w0 * p.stride + kw - p.pad,
-                        h0 * p.stride + kh - p.pad, img, kEvictNormal);
+                        h0 * p.stride + kh - p.pad, img, hint_a);
           } else {
-            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, kEvictNormal);
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, hint_a);
           }
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN, kEvictNormal);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN, hint_w);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -209,7 +229,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(tile, p.num_m, p.num_n, p.group_m, m_blk, n_blk);
+      tile_coords(tile, p.num_m, p.num_n, p.group_m, p.group_n, m_blk, n_blk);
       int row;
       bool row_ok;
       long long out_row;
@@ -268,7 +288,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 128; ++i) ss += x[i] * x[i];
             const float r = rsqrtf(ss * (1.0f / 128.0f) + e.eps);
-            const __nv_bfloat16* w = (head < e.Hq) ? (gen ? e.qw1 : e.qw0) : (gen ? e.kw1 : e.kw0);
+            const void* w = (head < e.Hq) ? (gen ? e.qw1 : e.qw0) : (gen ? e.kw1 : e.kw0);
+            const bool wf32 = e.fp32_flow >= 2;
             const float* cs = e.cos_t + out_row * 64;
             const float* sn = e.sin_t + out_row * 64;
 #pragma unroll
@@ -278,11 +299,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const float wa = __bfloat162float(w[i + u]), wb = __bfloat162float(w[64 + i + u]);
+                const float wa = wf32 ? static_cast<const float*>(w)[i + u]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[i + u]);
+                const float wb = wf32 ? static_cast<const float*>(w)[64 + i + u]
+                                      : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[64 + i + u]);
                 float ya, yb, oa, ob;
                 if (e.fp32_flow) {
-                  ya = __fmul_rn(wa, __fmul_rn(x[i + u], r));
-                  yb = __fmul_rn(wb, __fmul_rn(x[64 + i + u], r));
+                  const float na = (e.fp32_flow == 2) ? bf16_round(x[i + u] * r) : __fmul_rn(x[i + u], r);
+                  const float nb = (e.fp32_flow == 2) ? bf16_round(x[64 + i + u] * r) : __fmul_rn(x[64 + i + u], r);
+                  ya = __fmul_rn(wa, na);
+                  yb = __fmul_rn(wb, nb);
                   oa = __fadd_rn(__fmul_rn(ya, cc[u]), __fmul_rn(-yb, sv[u]));
                   ob = __fadd_rn(__fmul_rn(yb, cc[u]), __fmul_rn(ya, sv[u]));
                 } else {
@@ -332,7 +358,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (n0 + 32 <= p.N / 2) {
               uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), p.hints & 4);
             } else {
               for (int j = 0; j < 16; ++j)
                 if (n0 + 2 * j < p.N / 2) *reinterpret_cast<uint32_t*>(crow + c * 32 + 2 * j) = o[j];
@@ -343,6 +369,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0_tile = n_blk * BN;
         __nv_bfloat16* crow = p.C + out_row * p.ldc + n0_tile;
         const __nv_bfloat16* rrow = (EPI == EPI_RESID) ? p.resid + out_row * p.ldr + n0_tile : nullptr;
+        const float* rrow32 = (EPI == EPI_RESID_F32) ? p.resid32 + out_row * p.ldr + n0_tile : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -379,6 +406,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if constexpr (EPI == EPI_RESID) {
                 x0 = bf16_lo(rr[j]) + bf16_round(x0);
                 x1 = bf16_hi(rr[j]) + bf16_round(x1);
+              } else if constexpr (EPI == EPI_RESID_F32) {
+                if (n0 + 2 * j < p.N) {   // N % 8 == 0, so a pair is in or out together
+                  const float2 r2 = *reinterpret_cast<const float2*>(rrow32 + c * 32 + 2 * j);
+                  x0 = __fadd_rn(r2.x, bf16_round(x0));
+                  x1 = __fadd_rn(r2.y, bf16_round(x1));
+                }
               } else if constexpr (EPI == EPI_GELU) {
                 x0 = gelu_tanh_f(bf16_round(x0));
                 x1 = gelu_tanh_f(bf16_round(x1));
@@ -386,18 +419,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 x0 = silu_f(bf16_round(x0));
                 x1 = silu_f(bf16_round(x1));
               }
-              if constexpr (EPI == EPI_F32) {
+              if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
                 float* d32 = p.C32 + out_row * p.ldc + n0 + 2 * j;
                 if (n0 + 2 * j < p.N) *reinterpret_cast<float2*>(d32) = make_float2(x0, x1);
               }
               o[j] = pack_bf16x2(x0, x1);
             }
-            if constexpr (EPI == EPI_F32) {
+            if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
               // fp32 result already stored above
             } else if (full) {
               uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), p.hints & 4);
             } else {
               for (int j = 0; j < 16; ++j)
                 if (n0 + 2 * j < p.N) *reinterpret_cast<uint32_t*>(crow + c * 32 + 2 * j) = o[j];
@@ -441,7 +474,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   // (14-18 N-tiles: qkv, o_proj, down_proj) at 32; 8 and 64 lose 5-15 % either way.
   {
     static const int env_g = [] { const char* e = getenv("BAGEL_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
+    static const int env_n = [] { const char* e = getenv("BAGEL_GEMM_GROUP_N"); return e ? atoi(e) : -1; }();
+    static const int env_h = [] { const char* e = getenv("BAGEL_GEMM_HINTS"); return e ? atoi(e) : -1; }();
     p.group_m = env_g > 0 ? env_g : (p.num_n >= 64 ? 16 : 32);
+    // N super-tiles only where W does not fit the L2 beside the streams (gate|up: 272 MB); 0 / >= num_n = one sweep
+    int gn = env_n >= 0 ? env_n : 0;
+    if (gn <= 0 || gn > p.num_n) gn = p.num_n;
+    p.group_n = gn;
+    p.hints = env_h >= 0 ? env_h : 0;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
@@ -459,6 +499,7 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case EPI_GELU: return launch_gemm<BN, EPI_GELU>(tmA, tmB, p, s);
     case EPI_SILU: return launch_gemm<BN, EPI_SILU>(tmA, tmB, p, s);
     case EPI_F32: return launch_gemm<BN, EPI_F32>(tmA, tmB, p, s);
+    case EPI_RESID_F32: return launch_gemm<BN, EPI_RESID_F32>(tmA, tmB, p, s);
     default: return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: unknown epilogue %d", epi);
   }
 }
@@ -475,8 +516,8 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
     return set_error(BAGEL_ERR_ALIGN, "bagel_gemm_bf16: K, N and leading dims must be multiples of 8 (16 B)");
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)bias | (uintptr_t)resid) & 15)
     return set_error(BAGEL_ERR_ALIGN, "bagel_gemm_bf16: pointers must be 16-byte aligned");
-  if (epilogue == EPI_RESID && (resid == nullptr || (ldr % 8)))
-    return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: EPI_RESID needs resid with ldr %% 8 == 0");
+  if ((epilogue == EPI_RESID || epilogue == EPI_RESID_F32) && (resid == nullptr || (ldr % 8)))
+    return set_error(BAGEL_ERR_ARG, "bagel_gemm_bf16: the residual epilogues need resid with ldr %% 8 == 0");
   if (int rc = require_sm100()) return rc;
 
   GemmParams p{};
@@ -485,9 +526,10 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   p.ldc = ldc;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.resid32 = static_cast<const float*>(resid);   // BAGEL_EPI_RESID_F32: resid and C are fp32 [*, ldr] / [*, ldc]
   p.ldr = ldr;
   p.row_map = row_map;
-  p.C32 = static_cast<float*>(C);  // used by BAGEL_EPI_F32 only (C is then an fp32 [M, ldc] buffer)
+  p.C32 = static_cast<float*>(C);  // used by the fp32-output epilogues (C is then an fp32 [M, ldc] buffer)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   if (epilogue == EPI_SWIGLU && (N % 256))
@@ -589,8 +631,9 @@ extern "C" int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.row_map = row_map;
-  p.qkv.qw0 = static_cast<const __nv_bfloat16*>(q_w0); p.qkv.kw0 = static_cast<const __nv_bfloat16*>(k_w0);
-  p.qkv.qw1 = static_cast<const __nv_bfloat16*>(q_w1); p.qkv.kw1 = static_cast<const __nv_bfloat16*>(k_w1);
+  if (fp32_flow < 0 || fp32_flow > 3) return set_error(BAGEL_ERR_ARG, "bagel_gemm_qkv_norm_rope: flow must be 0..3");
+  p.qkv.qw0 = q_w0; p.qkv.kw0 = k_w0;
+  p.qkv.qw1 = q_w1; p.qkv.kw1 = k_w1;
   p.qkv.expert = expert; p.qkv.cos_t = cos_t; p.qkv.sin_t = sin_t;
   p.qkv.q_out = static_cast<__nv_bfloat16*>(q_out); p.qkv.k_out = static_cast<__nv_bfloat16*>(k_out);
   p.qkv.v_out = static_cast<__nv_bfloat16*>(v_out);

@@ -410,3 +410,17 @@ def taylor_eval(factors: torch.Tensor, n_factors: int, x: int, out: torch.Tensor
                                             out.stride(0), M, H, _stream())
     _cabi.check(rc, "bagel_taylor_eval_bf16")
     return out
+
+
+def siglip_rope2d(x: torch.Tensor, heads: int, head_stride: int, head_dim: int, pos_ids: torch.Tensor, cos_h, sin_h, cos_w,
+                  sin_w) -> None:
+    """In-place 2-D RoPE on `heads` consecutive heads of every row of x [n, >= heads*head_stride] (SigLIP rope=True)."""
+    _req(x, torch.bfloat16, "x"); _req(pos_ids, torch.int64, "pos_ids")
+    for t, nm in ((cos_h, "cos_h"), (sin_h, "sin_h"), (cos_w, "cos_w"), (sin_w, "sin_w")):
+        _req(t, torch.float32, nm)
+        assert t.is_contiguous() and t.shape[-1] == head_dim // 2
+    n = x.shape[0]
+    assert x.shape[1] >= heads * head_stride and pos_ids.numel() >= n
+    rc = _cabi.lib().bagel_siglip_rope2d_bf16(_ptr(x), x.stride(0), n, heads, head_stride, head_dim, _ptr(pos_ids), _ptr(cos_h),
+                                              _ptr(sin_h), _ptr(cos_w), _ptr(sin_w), _stream())
+    _cabi.check(rc, "bagel_siglip_rope2d_bf16")

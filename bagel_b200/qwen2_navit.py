@@ -112,7 +112,9 @@ class ForwardPlan:
         self.cu_k = torch.cat([z, tot.cumsum(0)]).to(dev, torch.int32)
         self.is_causal = bool(is_causal)
         self.mode = mode
-        self.fp32_flow = (mode == "gen")
+        # q/k-norm + RoPE arithmetic in fp32 only in PackedAttentionMoT's gen branch (qwen2_navit.py:542-548); the dense
+        # PackedAttention every other layer class uses is the bf16 flow whatever the mode (:325-336)
+        self.fp32_flow = (mode == "gen") and lm.layer_kind == "mot"
         self.q_rows = torch.as_tensor(packed_query_indexes).to(dev, torch.int32).contiguous()
         if self.n_ctx:
             self.ctx_rows = torch.as_tensor(packed_key_value_indexes).to(dev, torch.int32).contiguous()
@@ -139,7 +141,12 @@ class Qwen2Model:
     def __init__(self, config: Qwen2Config, device="cuda"):
         self.config = config
         self.device = torch.device(device)
-        self.use_moe = "Mo" in config.layer_module
+        # decoder layer class (reference Decoder_layer_dict, qwen2_navit.py:936-940)
+        kinds = {"Qwen2DecoderLayer": "dense", "Qwen2MoEDecoderLayer": "moe", "Qwen2MoTDecoderLayer": "mot"}
+        if config.layer_module not in kinds:
+            raise ValueError(f"unknown layer_module {config.layer_module!r}; expected one of {sorted(kinds)}")
+        self.layer_kind = kinds[config.layer_module]
+        self.use_moe = "Mo" in config.layer_module      # same test as the reference (:948): MoE and MoT
         self.enable_taylorseer = False
         self.fused_qkv = True   # head_dim 128: q/k-norm + RoPE + KV placement fused into the QKV GEMM epilogue
         self.layers: List[_Layer] = [_Layer() for _ in range(config.num_hidden_layers)]
@@ -213,6 +220,10 @@ class Qwen2Model:
         eps = cfg.rms_norm_eps
         routed = plan.expert is not None
         nt = plan.text_rows.numel() if (routed and plan.text_rows is not None) else 0
+        # MoT duplicates norms + attention + MLP per expert; MoE (Qwen2MoEDecoderLayer, :834-933) only the MLP
+        a_routed = routed and self.layer_kind == "mot"
+        a_expert = plan.expert if a_routed else None
+        nta = nt if a_routed else 0
 
         xa = self._buf("xa", n, H)
         xb = self._buf("xb", n, H)
@@ -229,36 +240,37 @@ class Qwen2Model:
             xa.copy_(x)
 
         for li, layer in enumerate(self.layers):
-            main = layer.gen if routed else layer.und
+            main = layer.gen if routed else layer.und       # MLP weights every row runs through
             und = layer.und
+            amain = layer.gen if a_routed else layer.und     # norm / attention weights every row runs through
             # ---- attention block ----
-            ops.rmsnorm(xa, und.ln_in, main.ln_in if routed else None, plan.expert, eps, out=h)
+            ops.rmsnorm(xa, und.ln_in, amain.ln_in if a_routed else None, a_expert, eps, out=h)
             if self.fused_qkv and D == 128:
                 # QKV GEMM with q/k-norm + RoPE + KV placement in its epilogue (no [n, 4608] round trip)
-                ops.gemm_qkv_norm_rope(h, main.wqkv, main.bqkv, und.q_norm, und.k_norm,
-                                       main.q_norm if routed else None, main.k_norm if routed else None, plan.expert,
+                ops.gemm_qkv_norm_rope(h, amain.wqkv, amain.bqkv, und.q_norm, und.k_norm,
+                                       amain.q_norm if a_routed else None, amain.k_norm if a_routed else None, a_expert,
                                        plan.cos, plan.sin, q, kbuf[li], vbuf[li], plan.q_rows, Hq, Hk, eps, plan.fp32_flow)
-                if nt:
+                if nta:
                     ops.copy_rows(h, ht, src_rows=plan.text_rows)
-                    ops.gemm_qkv_norm_rope(ht, und.wqkv, und.bqkv, und.q_norm, und.k_norm, main.q_norm, main.k_norm,
-                                           plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li], plan.q_rows, Hq, Hk,
+                    ops.gemm_qkv_norm_rope(ht, und.wqkv, und.bqkv, und.q_norm, und.k_norm, amain.q_norm, amain.k_norm,
+                                           a_expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li], plan.q_rows, Hq, Hk,
                                            eps, plan.fp32_flow, row_map=plan.text_rows)
             else:
-                ops.gemm(h, main.wqkv, bias=main.bqkv, out=qkv)
-                if nt:
+                ops.gemm(h, amain.wqkv, bias=amain.bqkv, out=qkv)
+                if nta:
                     ops.copy_rows(h, ht, src_rows=plan.text_rows)
                     ops.gemm(ht, und.wqkv, bias=und.bqkv, row_map=plan.text_rows, out=qkv)
-                ops.qk_norm_rope(qkv, und.q_norm, und.k_norm, main.q_norm if routed else None,
-                                 main.k_norm if routed else None, plan.expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li],
+                ops.qk_norm_rope(qkv, und.q_norm, und.k_norm, amain.q_norm if a_routed else None,
+                                 amain.k_norm if a_routed else None, a_expert, plan.cos, plan.sin, q, kbuf[li], vbuf[li],
                                  plan.q_rows, Hq, Hk, D, eps, plan.fp32_flow)
             ops.attn_varlen(q.view(n, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), plan.cu_q, plan.cu_k,
                             plan.max_q, plan.max_k, plan.is_causal, out=att.view(n, Hq, D))
-            ops.gemm(att, main.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
-            if nt:
+            ops.gemm(att, amain.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
+            if nta:
                 ops.copy_rows(att, at, src_rows=plan.text_rows)
                 ops.gemm(at, und.wo, resid=xa, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xb)
             # ---- MLP block ----
-            ops.rmsnorm(xb, und.ln_post, main.ln_post if routed else None, plan.expert, eps, out=h)
+            ops.rmsnorm(xb, und.ln_post, amain.ln_post if a_routed else None, a_expert, eps, out=h)
             ops.gemm(h, main.wgu, epilogue=ops.EPI_SWIGLU, out=act)
             ops.gemm(act, main.wd, resid=xb, epilogue=ops.EPI_RESID, out=xa)
             if nt:
@@ -351,6 +363,16 @@ class Qwen2ForCausalLM:
                 if sfx and not self.model.use_moe:
                     continue
                 e = _ExpertWeights()
+                if sfx and self.model.layer_kind == "moe":
+                    # Qwen2MoEDecoderLayer: only the MLP is duplicated (mlp_moe_gen); attention / norms are shared
+                    m = p + f"mlp{sfx}."
+                    e.wgu = ops.interleave_gate_up(get(m + "gate_proj.weight"), get(m + "up_proj.weight"))
+                    e.wd = get(m + "down_proj.weight").contiguous()
+                    u = layer.und
+                    e.wqkv, e.bqkv, e.wo, e.ln_in, e.ln_post, e.q_norm, e.k_norm = (u.wqkv, u.bqkv, u.wo, u.ln_in,
+                                                                                     u.ln_post, u.q_norm, u.k_norm)
+                    setattr(layer, tgt, e)
+                    continue
                 a = p + "self_attn."
                 e.wqkv = torch.cat([get(a + f"q_proj{sfx}.weight"), get(a + f"k_proj{sfx}.weight"),
                                     get(a + f"v_proj{sfx}.weight")], dim=0).contiguous()
@@ -361,7 +383,10 @@ class Qwen2ForCausalLM:
                     e.q_norm = get(a + f"q_norm{sfx}.weight").contiguous()
                     e.k_norm = get(a + f"k_norm{sfx}.weight").contiguous()
                 else:
-                    raise NotImplementedError("qk_norm=False is not used by any shipped BAGEL config")
+                    # nn.Identity in the reference (:247-252, :398-404); no shipped BAGEL config uses it and the fused
+                    # QKV epilogue has no norm-free variant, so say so at load time instead of mis-computing later
+                    raise NotImplementedError("bagel_b200: qk_norm=False is not implemented (every shipped BAGEL loader "
+                                              "forces qk_norm=True, app.py:41)")
                 m = p + f"mlp{sfx}."
                 e.wgu = ops.interleave_gate_up(get(m + "gate_proj.weight"), get(m + "up_proj.weight"))
                 e.wd = get(m + "down_proj.weight").contiguous()

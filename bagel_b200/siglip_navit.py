@@ -11,8 +11,10 @@ QKV weight is laid out with every head padded to 128 rows (zero weights/bias for
 kernel runs its d=128 path (softmax scale 72^-0.5 passed explicitly) and the out-projection weight carries zero
 columns for the padding. head_dim 64/128 towers run unpadded.
 
-`rope=True` (2-D RoPE, siglip_navit.py:102-142, 224-230) is disabled in every shipped inference config
-(app.py:45, eval/vlm/utils.py:37) and is not implemented in this round.
+`rope=True` (2-D RoPE, siglip_navit.py:102-142, 224-230; disabled in every shipped inference config, app.py:45,
+eval/vlm/utils.py:37): the tower then has no learned position table; q/k heads are rotated in place in the fused QKV
+buffer (bagel_siglip_rope2d_bf16: row table on the first half of a head, column table on the second half, fp32 tables
+built at construction exactly like RotaryEmbedding2D) between the QKV GEMM and the attention kernel.
 """
 from __future__ import annotations
 
@@ -30,6 +32,20 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def _rope2d_tables(dim: int, max_h: int, max_w: int, base: float = 10000.0):
+    """cos_h, sin_h, cos_w, sin_w fp32 [max_h*max_w, dim] — the buffers of the reference's RotaryEmbedding2D (:102-127),
+    same expressions on the host (construction time only)."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.int64).float() / dim))
+    grid_h = torch.arange(0, max_h).to(inv_freq.dtype)[:, None].repeat(1, max_w)
+    grid_w = torch.arange(0, max_w).to(inv_freq.dtype)[None, :].repeat(max_h, 1)
+    out = []
+    for grid in (grid_h, grid_w):
+        freqs = grid[..., None] * inv_freq[None, None, :]
+        emb = torch.cat((freqs, freqs), dim=-1).flatten(0, 1)
+        out += [emb.cos(), emb.sin()]
+    return tuple(out)
+
+
 class _Embeddings:
     def __init__(self, owner):
         self._owner = owner
@@ -42,10 +58,9 @@ class _Embeddings:
 
 class SiglipVisionTransformer:
     def __init__(self, config: SiglipVisionConfig, device="cuda"):
-        if getattr(config, "rope", False):
-            raise NotImplementedError("SigLIP 2-D RoPE (rope=True) is not used by any shipped BAGEL inference config")
         self.config = config
         self.device = torch.device(device)
+        self.rope = bool(getattr(config, "rope", False))
         self.embeddings = _Embeddings(self)
         H, nh = config.hidden_size, config.num_attention_heads
         self.head_dim = H // nh
@@ -57,6 +72,11 @@ class SiglipVisionTransformer:
         self.layers = []
         self.w = {}
         self._ws: Dict[str, torch.Tensor] = {}
+        if self.rope:
+            if self.head_dim % 4:
+                raise ValueError("SigLIP 2-D RoPE needs head_dim % 4 == 0")
+            side = config.image_size // config.patch_size
+            self.rope_tables = tuple(t.to(self.device).contiguous() for t in _rope2d_tables(self.head_dim // 2, side, side))
 
     def _buf(self, name, rows, cols):
         t = self._ws.get(name)
@@ -80,7 +100,8 @@ class SiglipVisionTransformer:
         wpad[:, : self.patch_dim] = pw
         self.w["patch_w"] = wpad
         self.w["patch_b"] = get("embeddings.patch_embedding.bias").contiguous()
-        self.w["pos"] = get("embeddings.position_embedding.weight").contiguous()
+        if not self.rope:   # rope=True towers have no learned position table (:164-165)
+            self.w["pos"] = get("embeddings.position_embedding.weight").contiguous()
         self.layers = []
         for li in range(cfg.num_hidden_layers):
             p = f"encoder.layers.{li}."
@@ -126,13 +147,18 @@ class SiglipVisionTransformer:
         att = self._buf("att", n, nh * dp)
         mid = self._buf("mid", n, cfg.intermediate_size)
         # patch embed + learned position embedding (siglip_navit.py:190-193)
-        ops.gemm(px, self.w["patch_w"], bias=self.w["patch_b"], out=h)
-        ops.latent_embed_add(h, None, self.w["pos"], pos, xa, None)
+        if self.rope:
+            ops.gemm(px, self.w["patch_w"], bias=self.w["patch_b"], out=xa)
+        else:
+            ops.gemm(px, self.w["patch_w"], bias=self.w["patch_b"], out=h)
+            ops.latent_embed_add(h, None, self.w["pos"], pos, xa, None)
         scale = float(self.head_dim) ** -0.5
         q3 = qkv.view(n, 3 * nh, dp)
         for L in self.layers:
             ops.layernorm(xa, L["layer_norm1_w"], L["layer_norm1_b"], eps, out=h)
             ops.gemm(h, L["wqkv"], bias=L["bqkv"], out=qkv)
+            if self.rope:   # q heads then k heads are the first 2*nh heads of the fused buffer
+                ops.siglip_rope2d(qkv, 2 * nh, dp, self.head_dim, pos, *self.rope_tables)
             ops.attn_varlen(q3[:, :nh], q3[:, nh:2 * nh], q3[:, 2 * nh:], cu, cu, int(max_seqlen), int(max_seqlen), False,
                             softmax_scale=scale, out=att.view(n, nh, dp))
             ops.gemm(att, L["wo"], bias=L["bo"], resid=xa, epilogue=ops.EPI_RESID, out=xb)

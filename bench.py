@@ -54,6 +54,11 @@ def parse_args():
     ap.add_argument("--e2e-no-graph", action="store_true", help="A/B: run the e2e generate_image without CUDA-graph capture")
     ap.add_argument("--no-taylorseer", action="store_true", help="skip the informational enable_taylorseer=True run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the blocks for the other BASELINE configs (attn, und_prefill, decode, edit, "
+                         "gpu_library_baseline, parity, strong_scaling)")
+    ap.add_argument("--blocks", default="attn,und,edit,library,strong",
+                    help="comma list of extra blocks to run (default: all)")
     return ap.parse_args()
 
 
@@ -172,24 +177,75 @@ def cpu_reference_sample(image_size: int, threads: int):
     return img_s, sample, t_layer, threads
 
 
+def cpu_reference_full_forward_flow(image_size: int, threads: int):
+    """ONE full velocity evaluation (`_forward_flow`, bagel.py:757-907) of ONE 1024^2 sample at BAGEL-7B dims on the
+    host cores with the oracle: latent-in, all 28 MoT layers (main branch, 66 cached context tokens), latent-out.
+    images/s = 1 / (t * 2 branches * 49 evaluations). The 28 layers share one set of random weights (the timing is
+    the same: 0.93 GB per layer does not stay in any CPU cache; drawing 14 G random parameters on the host would take
+    longer than the measurement)."""
+    import torch
+    from oracle import bagel_flow as obf, fixtures, qwen2_mot as om
+
+    torch.set_num_threads(threads)
+    c7 = fixtures.BAGEL_7B_LM
+    cfg1 = om.LMConfig(hidden_size=c7.hidden_size, intermediate_size=c7.intermediate_size, num_hidden_layers=1,
+                       num_attention_heads=c7.num_attention_heads, num_key_value_heads=c7.num_key_value_heads, vocab_size=8)
+    one = fixtures.lm_state_dict(cfg1, seed=0, dtype=torch.bfloat16, w_std=0.02, lm_head=False)
+    L = c7.num_hidden_layers
+    cfg = om.LMConfig(hidden_size=c7.hidden_size, intermediate_size=c7.intermediate_size, num_hidden_layers=L,
+                      num_attention_heads=c7.num_attention_heads, num_key_value_heads=c7.num_key_value_heads, vocab_size=8)
+    sd = {}
+    for k, v in one.items():
+        if k.startswith("model.layers.0."):
+            for li in range(L):
+                sd["language_model." + k.replace("model.layers.0.", f"model.layers.{li}.")] = v
+        else:
+            sd["language_model." + k] = v
+    sd.update(fixtures.bagel_extra_state_dict(cfg.hidden_size, seed=1, w_std=0.02))
+    sd["latent_pos_embed.pos_embed"] = obf.sincos_2d_table(cfg.hidden_size, 64).to(torch.bfloat16)
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=64)
+    ctx = 66
+    g = torch.Generator().manual_seed(3)
+    cache = om.KVCache(L)
+    for li in range(L):
+        cache.key_cache[li] = torch.randn(ctx, cfg.num_key_value_heads, cfg.head_dim, generator=g).to(torch.bfloat16)
+        cache.value_cache[li] = torch.randn(ctx, cfg.num_key_value_heads, cfg.head_dim, generator=g).to(torch.bfloat16)
+    torch.manual_seed(2)
+    gi = obf.prepare_vae_latent(fc, [ctx], [ctx], [(image_size, image_size)], 1, 2)
+    x = gi["packed_init_noises"]
+    t = torch.full((x.shape[0],), 0.9)
+    with torch.no_grad():
+        t0 = time.time()
+        obf.forward_flow(sd, fc, x, t, gi["packed_vae_token_indexes"], gi["packed_vae_position_ids"], gi["packed_text_ids"],
+                         gi["packed_text_indexes"], gi["packed_indexes"], gi["packed_position_ids"], gi["packed_seqlens"],
+                         gi["key_values_lens"], cache, gi["packed_key_value_indexes"])
+        dt = time.time() - t0
+    img_s = 1.0 / (dt * 2 * EVALS_PER_IMAGE)
+    sample = (f"oracle (CPU port of the reference path): ONE full _forward_flow (28 MoT layers, 1 sample, main CFG branch, "
+              f"{x.shape[0]} latent tokens + soi/eoi + {ctx} ctx) at {image_size}^2 = {dt:.1f} s on {threads} threads; "
+              f"images/s = 1/(t*2*49)")
+    return img_s, sample, dt
+
+
 def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        v, sample, t_layer, used = cpu_reference_sample(args.image_size, threads)
-        vals.append(v)
-    v = statistics.median(vals)
+    # thread count from the single-layer sweep (bf16 CPU matmuls are often fastest well below the core count), then one
+    # FULL velocity evaluation at that thread count as the measured sample
+    v1, sample1, t_layer, used = cpu_reference_sample(args.image_size, threads)
+    v, sample, t_full = cpu_reference_full_forward_flow(args.image_size, used)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / (v * EVALS_PER_IMAGE) * args.batch if v > 0 else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "BAGEL-7B-MoT random-init T2I 1024^2, 49 evals, text CFG (2 branches), CPU oracle port",
                    "global_batch": args.batch, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                         "extrapolated": True, "factor": 2 * EVALS_PER_IMAGE,
+                         "single_layer_cross_check": {"value": v1, "t_layer_s": t_layer, "factor": 28 * 2 * EVALS_PER_IMAGE}},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -374,12 +430,101 @@ def main():
                   "note": "generate_image(enable_taylorseer=True): the reference's TaylorSeer schedule computes 19 of "
                           "the 49 evaluations and extrapolates 30 (different numerics from the headline run)"}
 
+    # ---------------- the other BASELINE configs + library baseline + parity (tools/bench_blocks.py) ----------------
+    extra = {}
+    blocks = set() if args.no_extra or args.layers is not None else set(args.blocks.split(","))
+    if blocks:
+        from tools import bench_blocks as bb
+        torch.cuda.empty_cache()
+
+        def guarded(name, fn):
+            """A failing block must not take the headline line down with it: record the error instead."""
+            try:
+                return fn()
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                torch.cuda.synchronize()
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        if world == 1 and "library" in blocks:
+            tok = synthetic.RandomIdTokenizer(1 + rank)
+            prompt_ids = [tok.encode("64") for _ in range(B)]
+            r = guarded("library", lambda: bb.library_baseline_and_parity(model, gen_input, cfg_text, ctxs["main"], gen_kwargs,
+                                                                          prompt_ids, dev, ms_per_step, B))
+            extra.update(r if "error" not in r else {"gpu_library_baseline": r, "parity": r})
+            torch.cuda.empty_cache()
+        if world == 1 and "attn" in blocks:
+            extra["attn"] = guarded("attn", lambda: bb.attn_block(peaks, dev))
+        if world > 1 and "strong" in blocks and 8 % world == 0:
+            # configs[1] with the GLOBAL batch fixed at 8 images (SURVEY.md §8e: "cfg 2: B=8 -> 1/GPU")
+            def strong():
+                bs = 8 // world
+                gi_s, ct_s, cx_s = synthetic.t2i_inputs(model, bs, (args.image_size, args.image_size), seed=11 + rank,
+                                                        noise_seed=12 + rank)
+                kw_s = dict(gen_kwargs)
+                kw_s.update(cfg_text_packed_position_ids=ct_s["cfg_packed_position_ids"],
+                            cfg_text_packed_query_indexes=ct_s["cfg_packed_query_indexes"],
+                            cfg_text_key_values_lens=ct_s["cfg_key_values_lens"],
+                            cfg_text_packed_key_value_indexes=ct_s["cfg_packed_key_value_indexes"],
+                            cfg_text_past_key_values=cx_s["cfg_text"])
+                model.use_cuda_graph = False
+                rn = model.make_flow_runner(past_key_values=cx_s["main"], **gi_s, **kw_s)
+                for i in range(3):
+                    rn.step(i)
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ks = 8
+                for i in range(ks):
+                    rn.step(3 + i)
+                b.record()
+                torch.cuda.synchronize()
+                tt_ = torch.tensor([a.elapsed_time(b)], device=dev)
+                dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+                msps = float(tt_.item()) / ks
+                return {"workload": "BASELINE configs[1] strong-scaled: GLOBAL batch 8 images (SURVEY.md 8e), "
+                                    f"{bs} per GPU on {world} GPUs, 2 CFG branches", "global_batch": 8, "per_gpu_batch": bs,
+                        "steps": ks, "warmup": 3, "ms_per_step": msps, "value": 8 / (EVALS_PER_IMAGE * msps / 1e3),
+                        "unit": UNIT, "scaling": "strong"}
+            extra["strong_scaling"] = guarded("strong", strong)
+        need_vit = ("und" in blocks and world == 1) or "edit" in blocks
+        if need_vit:
+            r = guarded("vit", lambda: synthetic.attach_random_vit(model, seed=5))
+            if isinstance(r, dict):
+                extra["und_prefill"] = extra["edit"] = r
+                need_vit = False
+        if need_vit and world == 1 and "und" in blocks:
+            extra.update(guarded("und", lambda: bb.und_prefill_and_decode_block(model, dev)))
+            torch.cuda.empty_cache()
+        if need_vit and "edit" in blocks:
+            def edit():
+                vae = synthetic.build_random_vae(dev)
+                model.use_cuda_graph = True
+                if world > 1:
+                    dist.barrier()
+                r = bb.edit_block(model, vae, dev, samples=2)
+                tt_ = torch.tensor([r["seconds"]], device=dev)
+                if world > 1:
+                    dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+                sec = float(tt_.item())
+                return {"workload": "BASELINE configs[3]: image edit (VAE encode 1024^2 + SigLIP 980^2 + 64-token prompt, 49 "
+                                    "evals x 3 CFG branches, VAE decode) through InterleaveInferencer, 2 samples per GPU"
+                                    + (f" = batch {2 * world} over {world} GPUs, no collective" if world > 1 else ""),
+                        "global_batch": 2 * world, "seconds": sec, "s_per_image_per_gpu": sec / 2,
+                        "images_per_s": 2 * world / sec}
+            extra["edit"] = guarded("edit", edit)
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, sample, _, used = cpu_reference_sample(args.image_size, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample, "extrapolated": True,
+               "factor": 28 * 2 * EVALS_PER_IMAGE,
+               "note": "bounded sample (1 of 28 layers x 1 of 2 branches x 1 of 49 evaluations); `--impl reference` times one "
+                       "full _forward_flow (factor 98)"}
 
     if rank == 0:
         line = {
@@ -396,6 +541,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "e2e_taylorseer": e2e_ts,
         }
+        line.update(extra)
         if args.layers is not None:
             line["invalid"] = "debug run with a reduced layer count"
         _emit(line)

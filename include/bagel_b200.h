@@ -197,6 +197,14 @@ int bagel_taylor_update_bf16(const void* feature, long long ldf, void* factors, 
 int bagel_taylor_eval_bf16(const void* factors, long long plane_stride, int n_factors, int x, void* out, long long ldo,
                            int rows, int H, void* stream);
 
+/* SigLIP 2-D RoPE, in place on `heads` consecutive heads (head_stride elements apart, e.g. the q and k heads of a fused
+ * QKV buffer) of every token row (modeling/bagel/siglip_navit.py:102-142 RotaryEmbedding2D, :224-230): the first half of
+ * a head is rotated with the row table, the second half with the column table of the token's patch position:
+ *   out = bf16( fp32(x) * cos[pos] + rotate_half(fp32(x)) * sin[pos] ),   tables fp32 [max_h*max_w, head_dim/2]. */
+int bagel_siglip_rope2d_bf16(void* x, long long ld, int n_tokens, int heads, int head_stride, int head_dim,
+                             const long long* pos_ids, const float* cos_h, const float* sin_h, const float* cos_w,
+                             const float* sin_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

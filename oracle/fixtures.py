@@ -19,6 +19,10 @@ TINY_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, 
                    num_key_value_heads=2, vocab_size=1024)            # BASELINE.json configs[0]
 TINY128_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
                       num_key_value_heads=1, vocab_size=1024)         # same but head_dim 128 (7B's head_dim)
+TINY_DENSE_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, vocab_size=1024, layer_module="Qwen2DecoderLayer")
+TINY_MOE_LM = LMConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                       num_key_value_heads=1, vocab_size=1024, layer_module="Qwen2MoEDecoderLayer")   # head_dim 128
 BAGEL_7B_LM = LMConfig(hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
                        num_key_value_heads=4, vocab_size=152064)      # BAGEL-7B-MoT llm_config.json
 
@@ -29,7 +33,13 @@ def _normal(gen, shape, std):
 
 def lm_state_dict(cfg: LMConfig, seed: int = 0, dtype=torch.bfloat16, w_std: float = 0.05,
                   lm_head: bool = True) -> Dict[str, torch.Tensor]:
-    """Reference key names (qwen2_navit.py Qwen2ForCausalLM state_dict), MoT layers."""
+    """Reference key names (qwen2_navit.py Qwen2ForCausalLM state_dict) for cfg.layer_module: MoT layers carry every
+    module twice ("" / "_moe_gen"), MoE layers only the MLP, dense layers nothing extra."""
+    if cfg.layer_module != "Qwen2MoTDecoderLayer":
+        sd = lm_state_dict(LMConfig(**{**cfg.__dict__, "layer_module": "Qwen2MoTDecoderLayer"}), seed, dtype, w_std, lm_head)
+        moe = cfg.layer_module == "Qwen2MoEDecoderLayer"
+        return {k: v for k, v in sd.items()
+                if "_moe_gen" not in k or (moe and (".mlp_moe_gen." in k or k == "model.norm_moe_gen.weight"))}
     g = torch.Generator().manual_seed(seed)
     H, I, d = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
     Hq, Hk = cfg.num_attention_heads, cfg.num_key_value_heads

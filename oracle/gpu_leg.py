@@ -103,12 +103,9 @@ def flow_config(model) -> obf.FlowConfig:
 
 
 @torch.no_grad()
-def t2i_reference_run(sd, fc: obf.FlowConfig, prompt_ids, new_token_ids, gen_input, cfg_text_input, dev,
-                      x_trace=None, max_steps=None, **sampler_kw):
-    """The reference's text->image call order on `dev` with the oracle: prepare_prompts -> forward_cache_update_text
-    (main context; empty context for the text-CFG branch) -> generate_image. `gen_input` / `cfg_text_input` are the
-    dicts the product's packers returned (bit-identical to the reference's, tests/test_packers.py), so both sides
-    start from the same init noise."""
+def reference_contexts(sd, fc: obf.FlowConfig, prompt_ids, new_token_ids, gen_input, cfg_text_input, dev):
+    """Prefill exactly as the reference's text->image flow does (prepare_prompts -> forward_cache_update_text for the
+    main context; an empty context for the text-CFG branch). Returns (gen_input on dev, main cache, cfg_text branch dict)."""
     L = fc.lm.num_hidden_layers
     B = len(prompt_ids)
     gi_p, kv, rp = obf.prepare_prompts([0] * B, [0] * B, prompt_ids, new_token_ids["bos_token_id"],
@@ -119,4 +116,14 @@ def t2i_reference_run(sd, fc: obf.FlowConfig, prompt_ids, new_token_ids, gen_inp
     br = dict(packed_position_ids=ct["cfg_packed_position_ids"], packed_query_indexes=ct["cfg_packed_query_indexes"],
               key_values_lens=ct["cfg_key_values_lens"], past_key_values=om.KVCache(L),
               packed_key_value_indexes=ct["cfg_packed_key_value_indexes"])
+    return gi, cache, br
+
+
+@torch.no_grad()
+def t2i_reference_run(sd, fc: obf.FlowConfig, prompt_ids, new_token_ids, gen_input, cfg_text_input, dev,
+                      x_trace=None, max_steps=None, **sampler_kw):
+    """The reference's text->image call order on `dev` with the oracle: prefill (reference_contexts) -> generate_image.
+    `gen_input` / `cfg_text_input` are the dicts the product's packers returned (bit-identical to the reference's,
+    tests/test_packers.py), so both sides start from the same init noise."""
+    gi, cache, br = reference_contexts(sd, fc, prompt_ids, new_token_ids, gen_input, cfg_text_input, dev)
     return obf.generate_image(sd, fc, gi, cache, cfg_text=br, x_trace=x_trace, max_steps=max_steps, **sampler_kw)

@@ -66,6 +66,13 @@ class LMConfig:
     vocab_size: int
     rms_norm_eps: float = 1e-6
     rope_theta: float = 1000000.0
+    # decoder layer class (qwen2_navit.py:936-940): "Qwen2MoTDecoderLayer" (every module duplicated for the gen expert),
+    # "Qwen2MoEDecoderLayer" (:834-933 — shared attention / norms, only the MLP duplicated), "Qwen2DecoderLayer" (dense)
+    layer_module: str = "Qwen2MoTDecoderLayer"
+
+    @property
+    def use_moe(self) -> bool:
+        return "Mo" in self.layer_module          # qwen2_navit.py:948
 
     @property
     def head_dim(self) -> int:
@@ -152,6 +159,8 @@ def _attention(x, sd, cfg: LMConfig, li: int, cos, sin, query_lens, packed_query
     p = f"model.layers.{li}.self_attn."
     Hq, Hk, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
     eps = cfg.rms_norm_eps
+    if cfg.layer_module != "Qwen2MoTDecoderLayer":
+        mode = "und"        # dense PackedAttention (:313-378) is the und branch of PackedAttentionMoT, whatever the mode
     if mode == "und":
         q = linear(x, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"]).view(-1, Hq, d)
         k = linear(x, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"]).view(-1, Hk, d)
@@ -263,6 +272,21 @@ def _layer(x, sd, cfg, li, cos, sin, mode, vae_idx, text_idx, **attn_kw):
     p = f"model.layers.{li}."
     eps = cfg.rms_norm_eps
     resid = x
+    if cfg.layer_module != "Qwen2MoTDecoderLayer":
+        # Qwen2DecoderLayer (:603-684) / Qwen2MoEDecoderLayer (:834-933): one set of norms + attention for every token;
+        # the MoE layer routes only the MLP (text rows -> mlp, latent rows -> mlp_moe_gen) in mode "gen"
+        h = rms_norm(x, sd[p + "input_layernorm.weight"], eps)
+        a = _attention(h, sd, cfg, li, cos, sin, mode="und", vae_idx=vae_idx, text_idx=text_idx, **attn_kw)
+        x = resid + a
+        resid = x
+        h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], eps)
+        if mode == "und" or cfg.layer_module == "Qwen2DecoderLayer":
+            m = swiglu_mlp(h, sd, p + "mlp.")
+        else:
+            m = torch.zeros_like(h).to(BF16 if _AUTOCAST[0] == BF16 else h.dtype)
+            m[text_idx] = swiglu_mlp(h[text_idx], sd, p + "mlp.")
+            m[vae_idx] = swiglu_mlp(h[vae_idx], sd, p + "mlp_moe_gen.")
+        return resid + m
     if mode == "und":
         h = rms_norm(x, sd[p + "input_layernorm.weight"], eps)
     else:
@@ -310,7 +334,7 @@ def lm_forward_inference(sd: Dict[str, torch.Tensor], cfg: LMConfig, packed_quer
     if taylor is not None:
         taylor.step += 1
     eps = cfg.rms_norm_eps
-    if mode == "und":
+    if mode == "und" or not cfg.use_moe:
         x = rms_norm(x, sd["model.norm.weight"], eps)
     else:
         y = torch.zeros_like(x)

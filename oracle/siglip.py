@@ -24,6 +24,8 @@ class VitConfig:
     patch_size: int = 14
     num_channels: int = 3
     layer_norm_eps: float = 1e-6
+    rope: bool = False          # 2-D RoPE on q/k (siglip_navit.py:102-142, 224-230); off in every shipped loader
+    image_size: int = 980       # RoPE table side = image_size // patch_size (:343-345)
 
 
 def patchify(image, p):
@@ -37,10 +39,34 @@ def layer_norm(x, w, b, eps):
     return F.layer_norm(x, (x.shape[-1],), w.to(x.dtype), b.to(x.dtype), eps)
 
 
+def rope2d_tables(dim, max_h, max_w, base=10000):
+    """RotaryEmbedding2D (siglip_navit.py:102-127): fp32 buffers cos_h, sin_h, cos_w, sin_w of shape [max_h*max_w, dim]."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.int64).float() / dim))
+    grid_h = torch.arange(0, max_h).to(inv_freq.dtype)[:, None].repeat(1, max_w)
+    grid_w = torch.arange(0, max_w).to(inv_freq.dtype)[None, :].repeat(max_h, 1)
+
+    def side(grid):
+        freqs = grid[..., None] * inv_freq[None, None, :]
+        emb = torch.cat((freqs, freqs), dim=-1).flatten(0, 1)
+        return emb.cos(), emb.sin()
+
+    return (*side(grid_h), *side(grid_w))
+
+
+def _rot_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
 def vit_forward(sd, vc: VitConfig, pixels, pos_ids, seqlens, pfx="vit_model.vision_model."):
-    """siglip_navit.py:184-195, 216-243, 255-258, 283-298, 354-371 (rope=False)."""
+    """siglip_navit.py:184-195, 216-243, 255-258, 283-298, 354-371."""
+    if vc.rope:
+        side = vc.image_size // vc.patch_size
+        cos_h, sin_h, cos_w, sin_w = (t[pos_ids].unsqueeze(1) for t in
+                                      rope2d_tables(vc.hidden_size // vc.num_attention_heads // 2, side, side))
     x = linear(pixels, sd[pfx + "embeddings.patch_embedding.weight"], sd[pfx + "embeddings.patch_embedding.bias"])
-    x = x + sd[pfx + "embeddings.position_embedding.weight"][pos_ids]
+    if not vc.rope:     # with rope=True the tower has no learned position table at all (:164-165, 191-194)
+        x = x + sd[pfx + "embeddings.position_embedding.weight"][pos_ids]
     nh = vc.num_attention_heads
     d = vc.hidden_size // nh
     lens = [int(v) for v in seqlens]
@@ -50,6 +76,11 @@ def vit_forward(sd, vc: VitConfig, pixels, pos_ids, seqlens, pfx="vit_model.visi
         q = linear(h, sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.q_proj.bias"]).view(-1, nh, d)
         k = linear(h, sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"]).view(-1, nh, d)
         v = linear(h, sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"]).view(-1, nh, d)
+        if vc.rope:     # :224-230 — halves of head_dim rotated by the row / column tables (fp32 buffers => fp32 math)
+            qh, qw, kh, kw = q[..., : d // 2], q[..., d // 2:], k[..., : d // 2], k[..., d // 2:]
+            qh, kh = qh * cos_h + _rot_half(qh) * sin_h, kh * cos_h + _rot_half(kh) * sin_h
+            qw, kw = qw * cos_w + _rot_half(qw) * sin_w, kw * cos_w + _rot_half(kw) * sin_w
+            q, k = torch.cat([qh, qw], dim=-1), torch.cat([kh, kw], dim=-1)
         dt = om._AUTOCAST[0]
         a = om.varlen_attention(q.to(dt), k.to(dt), v.to(dt), lens, lens, False).reshape(-1, nh * d)
         x = x + linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])

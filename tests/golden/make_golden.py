@@ -37,7 +37,8 @@ def ref_lm(ns, cfg, sd, dtype):
     rcfg = ref_shims.make_llm_config(
         ns, vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
         num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
-        num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta, max_position_embeddings=32768)
+        num_key_value_heads=cfg.num_key_value_heads, rope_theta=cfg.rope_theta, max_position_embeddings=32768,
+        layer_module=cfg.layer_module)
     lm = ref_shims.cast_parameters(ns.qwen2_navit.Qwen2ForCausalLM(rcfg).eval(), dtype)
     lm.load_state_dict(sd, strict=True)
     return lm, rcfg
@@ -464,16 +465,138 @@ def fc_of(cfg):
     return obf.FlowConfig(lm=cfg, max_latent_size=8)
 
 
+def golden_lm_variants(ns):
+    """The two other decoder-layer classes of Decoder_layer_dict (qwen2_navit.py:936-940): dense Qwen2DecoderLayer /
+    PackedAttention (:236-378, 603-684) and Qwen2MoEDecoderLayer (:834-933). Causal und prefill (cache update), then a
+    non-causal forward on top of the cache in mode "gen" (MoE routes the MLP; the dense model ignores the mode)."""
+    out = {}
+    for tag, cfg in (("dense", fixtures.TINY_DENSE_LM), ("moe", fixtures.TINY_MOE_LM)):
+        dtype = torch.bfloat16
+        sd = fixtures.lm_state_dict(cfg, seed=0, dtype=dtype)
+        lm, _ = ref_lm(ns, cfg, sd, dtype)
+        inp = fixtures.config1_inputs(cfg, dtype=dtype)
+        n = 130
+        xg = torch.randn(n, cfg.hidden_size, generator=torch.Generator().manual_seed(5)).to(dtype)
+        kw = dict(query_lens=torch.tensor([n], dtype=torch.int32),
+                  packed_query_position_ids=torch.full((n,), 512, dtype=torch.long),
+                  packed_query_indexes=torch.arange(512, 512 + n), key_values_lens=torch.tensor([512], dtype=torch.int32),
+                  packed_key_value_indexes=torch.arange(512), update_past_key_values=False, is_causal=False, mode="gen",
+                  packed_vae_token_indexes=torch.arange(1, n - 1), packed_text_indexes=torch.tensor([0, n - 1]))
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            cache = ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers)
+            und = lm.forward_inference(
+                packed_query_sequence=inp["x"], query_lens=inp["query_lens"],
+                packed_query_position_ids=inp["und_position_ids"], packed_query_indexes=inp["query_indexes"],
+                past_key_values=cache, key_values_lens=torch.tensor([0], dtype=torch.int32),
+                packed_key_value_indexes=torch.zeros(0, dtype=torch.long), update_past_key_values=True, is_causal=True,
+                mode="und")
+            gen = lm.forward_inference(packed_query_sequence=xg, past_key_values=cache, **kw)
+        with torch.no_grad():
+            oc = om.KVCache(cfg.num_hidden_layers)
+            oh, oc = om.lm_forward_inference(sd, cfg, inp["x"], inp["query_lens"], inp["und_position_ids"],
+                                             inp["query_indexes"], oc, torch.tensor([0], dtype=torch.int32),
+                                             torch.zeros(0, dtype=torch.long), True, True, "und")
+            og, _ = om.lm_forward_inference(sd, cfg, xg, past_key_values=oc, **kw)
+        assert torch.equal(oh, und.packed_query_sequence) and torch.equal(og, gen.packed_query_sequence), \
+            f"oracle != reference ({tag})"
+        for li in range(cfg.num_hidden_layers):
+            assert torch.equal(oc.key_cache[li], cache.key_cache[li]) and torch.equal(oc.value_cache[li], cache.value_cache[li])
+        out[tag + ".und_hidden"] = und.packed_query_sequence.contiguous()
+        out[tag + ".gen_hidden"] = gen.packed_query_sequence.contiguous()
+        out[tag + ".k_cache_last"] = cache.key_cache[cfg.num_hidden_layers - 1].contiguous()
+        out[tag + ".v_cache_last"] = cache.value_cache[cfg.num_hidden_layers - 1].contiguous()
+        print(f"lm_variants {tag} ({cfg.layer_module}): oracle == reference (bit-exact)")
+    save_file(out, os.path.join(OUT, "lm_variants.safetensors"))
+
+
+def _ref_bagel_with_vit(ns, rope):
+    cfg = fixtures.TINY_LM
+    dtype = torch.bfloat16
+    tv = fixtures.TINY_VIT
+    sd = flow_state_dict(cfg, dtype)
+    sd.update(fixtures.vit_state_dict(tv["hidden"], tv["inter"], tv["layers"], tv["heads"], cfg.hidden_size, dtype=dtype))
+    lm_sd = {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}
+    lm, rcfg = ref_lm(ns, cfg, lm_sd, dtype)
+    sn = ns.siglip_navit
+    vcfg = sn.SiglipVisionConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                                 num_attention_heads=tv["heads"], num_channels=3, image_size=112, patch_size=14, rope=rope)
+    vit = sn.SiglipVisionModel(vcfg)
+    vit.vision_model.embeddings.convert_conv2d_to_linear(vcfg)
+    bcfg = ns.bagel.BagelConfig(visual_gen=True, visual_und=True, llm_config=rcfg, vit_config=vcfg,
+                                vae_config=SimpleNamespace(downsample=8, z_channels=16), latent_patch_size=2,
+                                max_latent_size=8, vit_max_num_patch_per_side=8)
+    model = ns.bagel.Bagel(lm, vit, bcfg).eval()
+    ref_shims.cast_parameters(model, dtype)
+    missing = model.load_state_dict(sd, strict=False)
+    # rope=True: no learned position table in the tower (its key is then unexpected), RoPE tables are buffers
+    assert all("position_embedding" in k for k in missing.unexpected_keys) and (rope or not missing.unexpected_keys), missing
+    assert all("pos_embed" in k or ".rope." in k for k in missing.missing_keys), missing
+    sd_full = dict(sd)
+    sd_full["latent_pos_embed.pos_embed"] = model.latent_pos_embed.pos_embed.data.clone()
+    sd_full["vit_pos_embed.pos_embed"] = model.vit_pos_embed.pos_embed.data.clone()
+    return model, sd_full, cfg, tv
+
+
+def golden_vit_rope(ns):
+    """SigLIP tower with the optional 2-D RoPE enabled (siglip_navit.py:102-142, 224-230, 343-365): same weights and
+    images as vit_tiny.safetensors, config.rope=True, head_dim 72 -> 36-wide row / column halves."""
+    from oracle import siglip as osl
+    model, sd_full, cfg, tv = _ref_bagel_with_vit(ns, rope=True)
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"], rope=True, image_size=112)
+    images = fixtures.vit_images()
+    gi, kv, rp = model.prepare_vit_images([0, 0], [0, 0], images, lambda im: im, NEW_TOKEN_IDS)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        cu = torch.nn.functional.pad(torch.cumsum(gi["vit_token_seqlens"], 0), (1, 0)).to(torch.int32)
+        feats = model.vit_model(packed_pixel_values=gi["packed_vit_tokens"],
+                                packed_flattened_position_ids=gi["packed_vit_position_ids"], cu_seqlens=cu,
+                                max_seqlen=int(gi["vit_token_seqlens"].max()))
+    with torch.no_grad():
+        ofeats = osl.vit_forward(sd_full, vc, gi["packed_vit_tokens"], gi["packed_vit_position_ids"], gi["vit_token_seqlens"])
+    assert torch.equal(feats, ofeats), "oracle ViT (rope=True) != reference"
+    print("ViT tower rope=True: oracle == reference (bit-exact); feature |x| mean", float(feats.float().abs().mean()))
+    save_file({"vit_rope.features": feats.contiguous()}, os.path.join(OUT, "vit_rope_tiny.safetensors"))
+
+
+def golden_chat(ns):
+    """Bagel.chat (bagel.py:1004-1075): two images + a prompt -> greedy text, through the reference's own method."""
+    model, sd_full, cfg, tv = _ref_bagel_with_vit(ns, rope=False)
+    tok = fixtures.ToyTokenizer()
+    images = fixtures.vit_images()
+    import warnings
+    logits = []
+    hook = model.language_model.lm_head.register_forward_hook(lambda m, i, o: logits.append(o.detach().clone()))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            text = model.chat(tok, dict(NEW_TOKEN_IDS), lambda im: im, images, "5 17 900 33 2 describe", max_length=8,
+                              do_sample=False)
+    hook.remove()
+    lg = torch.stack([x.reshape(-1) for x in logits], 0)          # [steps, V] (one sample)
+    top2 = lg.float().topk(2, dim=-1).values
+    print("chat:", repr(text), "| top-1/top-2 logit margins per step:", [round(float(x), 3) for x in top2[:, 0] - top2[:, 1]])
+    save_file({"chat.text": torch.tensor(list(text.encode("utf-8")), dtype=torch.uint8), "chat.logits": lg.contiguous()},
+              os.path.join(OUT, "chat_tiny.safetensors"))
+
+
 def main():
     if not ref_shims.reference_available():
         raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
     torch.set_num_threads(8)
     ns = ref_shims.load_reference()
+    if "--new-only" in sys.argv:    # round-2 additions only (leaves the round-1 fixture files untouched)
+        golden_lm_variants(ns)
+        golden_vit_rope(ns)
+        golden_chat(ns)
+        return
     golden_lm_config1(ns)
     golden_flow(ns)
     golden_vit(ns)
     golden_vae(ns)
     golden_inferencer(ns)
+    golden_lm_variants(ns)
+    golden_vit_rope(ns)
+    golden_chat(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

@@ -22,7 +22,7 @@ def test_header_and_bindings_agree(lib):
 
 
 def test_abi_version_and_counters(lib):
-    assert lib.bagel_abi_version() == 2
+    assert lib.bagel_abi_version() == 3
     assert lib.bagel_launch_count() >= 0
     assert isinstance(lib.bagel_last_error(), bytes)
 
