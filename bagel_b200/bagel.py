@@ -83,6 +83,9 @@ class Bagel:
         self.language_model = language_model
         self.config = config
         self.device = language_model.device
+        # "A": bf16 weights + autocast (app.py:111); "B": fp32 master weights + autocast (eval drivers) — see qwen2_navit.py
+        self.dtype_mode = language_model.model.dtype_mode
+        sdt = language_model.model.stream_dtype
         llm = config.llm_config
         self.hidden_size = llm.hidden_size
         self.use_moe = "Mo" in llm.layer_module
@@ -97,14 +100,14 @@ class Bagel:
             self.time_embedder = TimestepEmbedder(self.hidden_size)
             self.vae2llm = _Affine()
             self.llm2vae = _Affine()
-            self.latent_pos_embed = PositionEmbedding(self.max_latent_size, self.hidden_size, self.device)
+            self.latent_pos_embed = PositionEmbedding(self.max_latent_size, self.hidden_size, self.device, sdt)
         if config.visual_und:
             self.vit_model = vit_model
             self.vit_patch_size = config.vit_config.patch_size
             self.vit_max_num_patch_per_side = config.vit_max_num_patch_per_side
             self.vit_hidden_size = config.vit_config.hidden_size
             self.connector = MLPconnector(self.vit_hidden_size, self.hidden_size, config.connector_act)
-            self.vit_pos_embed = PositionEmbedding(self.vit_max_num_patch_per_side, self.hidden_size, self.device)
+            self.vit_pos_embed = PositionEmbedding(self.vit_max_num_patch_per_side, self.hidden_size, self.device, sdt)
         self.get_flattened_position_ids = (get_flattened_position_ids_interpolate if config.interpolate_pos
                                            else get_flattened_position_ids_extrapolate)
         self.use_cuda_graph = True
@@ -292,6 +295,9 @@ class Bagel:
                                  packed_key_value_indexes, key_values_lens):
         dev = self.device
         lm = self.language_model.model
+        if self.dtype_mode == "B":
+            raise NotImplementedError("dtype_mode='B' covers the LM, the text / VAE prefills and the sampler; the SigLIP tower "
+                                      "runs its bf16-stream path only (mode A)")
         n = int(torch.as_tensor(packed_seqlens).sum())
         seq = torch.zeros((n, self.hidden_size), dtype=BF16, device=dev)
         emb = lm.embed_tokens(torch.as_tensor(packed_text_ids))
@@ -357,10 +363,11 @@ class Bagel:
                                  packed_seqlens, packed_indexes, key_values_lens, packed_key_value_indexes):
         dev = self.device
         lm = self.language_model.model
+        modeB = self.dtype_mode == "B"
         n = int(torch.as_tensor(packed_seqlens).sum())
-        seq = torch.zeros((n, self.hidden_size), dtype=BF16, device=dev)
+        seq = torch.zeros((n, self.hidden_size), dtype=lm.stream_dtype, device=dev)
         emb = lm.embed_tokens(torch.as_tensor(packed_text_ids))
-        ops.copy_rows(emb, seq, dst_rows=torch.as_tensor(packed_text_indexes).to(dev, torch.int32))
+        (ops.copy_rows_f32 if modeB else ops.copy_rows)(emb, seq, dst_rows=torch.as_tensor(packed_text_indexes).to(dev, torch.int32))
         latents = vae_model.encode(padded_images)                      # [B, z, Hm/8, Wm/8]
         p, zc = self.latent_patch_size, self.latent_channel
         rows = []
@@ -370,9 +377,10 @@ class Bagel:
         packed_latent = torch.cat(rows, dim=0).to(dev, BF16).contiguous()
         proj = ops.gemm(packed_latent, self.vae2llm.weight, bias=self.vae2llm.bias)
         t_emb = self.time_embedder(torch.as_tensor(packed_timesteps).to(dev, torch.float32).reshape(-1)[:1])
-        ops.latent_embed_add(proj, t_emb[0], self.latent_pos_embed.pos_embed,
-                             torch.as_tensor(packed_vae_position_ids).to(dev, torch.int64).contiguous(), seq,
-                             torch.as_tensor(packed_vae_token_indexes).to(dev, torch.int32))
+        (ops.latent_embed_add_f32 if modeB else ops.latent_embed_add)(
+            proj, t_emb[0], self.latent_pos_embed.pos_embed,
+            torch.as_tensor(packed_vae_position_ids).to(dev, torch.int64).contiguous(), seq,
+            torch.as_tensor(packed_vae_token_indexes).to(dev, torch.int32))
         extra = {}
         if self.use_moe:
             extra = dict(mode="gen", packed_vae_token_indexes=packed_vae_token_indexes,
@@ -434,13 +442,15 @@ class Bagel:
         lm = self.language_model.model
         plan, kbuf, vbuf, nb = st[key]
         n = st["n"]
-        seq = lm._buf("xa", plan.n, self.hidden_size)
+        modeB = self.dtype_mode == "B"
+        embed_add = ops.latent_embed_add_f32 if modeB else ops.latent_embed_add
+        copy_rows = ops.copy_rows_f32 if modeB else ops.copy_rows
+        seq = lm._buf("xa", plan.n, self.hidden_size, lm.stream_dtype)
         ops.cast_f32_to_bf16(x_src, out=st["x_bf16"])
         ops.gemm(st["x_bf16"], self.vae2llm.weight, bias=self.vae2llm.bias, out=st["proj"])
         for b in range(nb):
-            ops.latent_embed_add(st["proj"], t_row, self.latent_pos_embed.pos_embed, st["vae_pos"],
-                                 seq[b * n:(b + 1) * n], st["vae_rows"])
-            ops.copy_rows(st["text_emb"], seq[b * n:(b + 1) * n], dst_rows=st["text_rows"])
+            embed_add(st["proj"], t_row, self.latent_pos_embed.pos_embed, st["vae_pos"], seq[b * n:(b + 1) * n], st["vae_rows"])
+            copy_rows(st["text_emb"], seq[b * n:(b + 1) * n], dst_rows=st["text_rows"])
         lm.run_layers(seq, plan, kbuf, vbuf, final_norm=False)
         if head:
             self._velocity_head(st, key)
@@ -450,7 +460,7 @@ class Bagel:
         """Final norm + llm2vae (bagel.py:832) over the hidden state in the LM's "xa" workspace."""
         lm = self.language_model.model
         plan, _, _, nb = st[key]
-        out = lm.final_norm(plan)
+        out = lm.final_norm(plan, for_linear=True)
         ops.gemm(out, self.llm2vae.weight, bias=self.llm2vae.bias, out=st["v_all"][: nb * st["n"]])
 
     def _cfg_update(self, st: Dict[str, Any], nb: int, scales: Tuple[float, float], renorm_min: float,
@@ -501,6 +511,8 @@ class Bagel:
         velocity evaluation + CFG + Euler update number i as a sync-free kernel sequence."""
         if cfg_renorm_type not in ops.RENORM:
             raise NotImplementedError(f"{cfg_renorm_type} is not supported")
+        if enable_taylorseer and self.dtype_mode == "B":
+            raise NotImplementedError("enable_taylorseer=True is implemented for dtype_mode='A' only (bf16 factor planes)")
         dev = self.device
 
         # ---- schedule (host; identical arithmetic to the reference :693-696) ----
@@ -568,6 +580,8 @@ class Bagel:
         The only host<->device traffic per step is the 8-byte EOS check the reference also performs."""
         dev = self.device
         lm = self.language_model.model
+        if self.dtype_mode == "B":
+            raise NotImplementedError("generate_text: the device-resident decode loop is implemented for dtype_mode='A'")
         cfg = lm.config
         L, H, Hq, Hk, D = cfg.num_hidden_layers, cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         w = Hk * D

@@ -37,14 +37,16 @@ def sincos_2d_table(embed_dim: int, grid_size: int) -> torch.Tensor:
 class PositionEmbedding:
     """Frozen table looked up by flattened (row*max_side+col) ids (reference :127-144)."""
 
-    def __init__(self, max_num_patch_per_side: int, hidden_size: int, device="cuda"):
+    def __init__(self, max_num_patch_per_side: int, hidden_size: int, device="cuda", dtype=BF16):
+        """dtype: bf16 when the checkpoint is cast to bf16 (mode A), fp32 with fp32 master weights (mode B)."""
         self.max_num_patch_per_side = max_num_patch_per_side
         self.hidden_size = hidden_size
-        self.pos_embed = sincos_2d_table(hidden_size, max_num_patch_per_side).to(device, BF16).contiguous()
+        self.dtype = dtype
+        self.pos_embed = sincos_2d_table(hidden_size, max_num_patch_per_side).to(device, dtype).contiguous()
 
     def load(self, t: Optional[torch.Tensor]):
         if t is not None:
-            self.pos_embed = t.to(self.pos_embed.device, BF16).contiguous()
+            self.pos_embed = t.to(self.pos_embed.device, self.dtype).contiguous()
 
 
 def timestep_sinusoid(t: torch.Tensor, dim: int = 256, max_period: float = 10000.0) -> torch.Tensor:

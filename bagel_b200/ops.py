@@ -10,6 +10,7 @@ import torch
 from . import _cabi
 
 EPI_BIAS, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_SILU, EPI_F32 = 0, 1, 2, 3, 4, 5
+EPI_RESID_F32 = 7   # fp32 residual stream (dtype mode B): out32 = resid32 + bf16(acc + bias)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -74,7 +75,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     N = w.shape[0]
     assert w.shape[1] == K
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
-    out_dtype = torch.float32 if epilogue == EPI_F32 else torch.bfloat16
+    out_dtype = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32) else torch.bfloat16
     if out is None:
         assert row_map is None, "row_map scatter needs an explicit `out`"
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
@@ -85,7 +86,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         assert bias.numel() == N
     ldr = 0
     if resid is not None:
-        _req(resid, torch.bfloat16, "resid")
+        _req(resid, torch.float32 if epilogue == EPI_RESID_F32 else torch.bfloat16, "resid")
         ldr = resid.stride(0)
     if row_map is not None:
         _req(row_map, torch.int32, "row_map")
@@ -110,7 +111,7 @@ def gemm_qkv_norm_rope(a, w, bias, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_o
     M, K = a.shape
     assert w.shape == ((Hq + 2 * Hk) * 128, K)
     _qkv_tail_checks(M if row_map is None else None, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows,
-                     Hq, Hk, 128)
+                     Hq, Hk, 128, int(fp32_flow))
     _opt(row_map, torch.int32, "row_map")
     rc = _cabi.lib().bagel_gemm_qkv_norm_rope(
         _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), M, K, _ptr(row_map), _ptr(q_w0), _ptr(k_w0),
@@ -119,12 +120,13 @@ def gemm_qkv_norm_rope(a, w, bias, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_o
     _cabi.check(rc, "bagel_gemm_qkv_norm_rope")
 
 
-def _qkv_tail_checks(n_rows, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D):
+def _qkv_tail_checks(n_rows, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D, flow=0):
     """Shared argument checks of the two q/k-norm + RoPE + KV-placement entry points (raw pointers cross the C ABI)."""
+    wdt = torch.float32 if flow >= 2 else torch.bfloat16      # flows 2, 3 (fp32 master weights) read fp32 norm weights
     for t, nm in ((q_w0, "q_w0"), (k_w0, "k_w0")):
-        _req(t, torch.bfloat16, nm)
+        _req(t, wdt, nm)
         assert t.numel() == D, f"{nm}: expected {D} elements"
-    _opt(q_w1, torch.bfloat16, "q_w1"); _opt(k_w1, torch.bfloat16, "k_w1")
+    _opt(q_w1, wdt, "q_w1"); _opt(k_w1, wdt, "k_w1")
     _opt(expert, torch.uint8, "expert")
     _req(cos, torch.float32, "cos"); _req(sin, torch.float32, "sin")
     assert cos.shape == sin.shape and cos.shape[-1] == D // 2 and cos.is_contiguous() and sin.is_contiguous()
@@ -213,7 +215,7 @@ def qk_norm_rope(qkv, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_
     _req(qkv, torch.bfloat16, "qkv")
     N = qkv.shape[0]
     assert qkv.shape[1] >= (Hq + 2 * Hk) * D
-    _qkv_tail_checks(N, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D)
+    _qkv_tail_checks(N, q_w0, k_w0, q_w1, k_w1, expert, cos, sin, q_out, k_out, v_out, kv_rows, Hq, Hk, D, int(fp32_flow))
     rc = _cabi.lib().bagel_qk_norm_rope(_ptr(qkv), qkv.stride(0), _ptr(q_w0), _ptr(k_w0), _ptr(q_w1), _ptr(k_w1),
                                         _ptr(expert), _ptr(cos), _ptr(sin), _ptr(q_out), q_out.stride(0), _ptr(k_out),
                                         _ptr(v_out), k_out.stride(0), _ptr(kv_rows), N, Hq, Hk, D, float(eps),
@@ -424,3 +426,35 @@ def siglip_rope2d(x: torch.Tensor, heads: int, head_stride: int, head_dim: int, 
     rc = _cabi.lib().bagel_siglip_rope2d_bf16(_ptr(x), x.stride(0), n, heads, head_stride, head_dim, _ptr(pos_ids), _ptr(cos_h),
                                               _ptr(sin_h), _ptr(cos_w), _ptr(sin_w), _stream())
     _cabi.check(rc, "bagel_siglip_rope2d_bf16")
+
+
+def rmsnorm_f32(x: torch.Tensor, w0: torch.Tensor, w1: Optional[torch.Tensor] = None, expert: Optional[torch.Tensor] = None,
+                eps: float = 1e-6, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """dtype mode B: fp32 hidden stream, fp32 norm weights; bf16 out (the next Linear's input) or fp32 out."""
+    _req(x, torch.float32, "x"); _req(w0, torch.float32, "w0"); _opt(w1, torch.float32, "w1"); _opt(expert, torch.uint8, "expert")
+    N, H = x.shape
+    if out is None:
+        out = torch.empty((N, H), dtype=out_dtype, device=x.device)
+    assert out.dtype in (torch.bfloat16, torch.float32) and out.shape[0] >= N and out.shape[1] == H and out.stride(1) == 1
+    rc = _cabi.lib().bagel_rmsnorm_f32(_ptr(x), x.stride(0), _ptr(w0), _ptr(w1), _ptr(expert), _ptr(out), out.stride(0),
+                                       int(out.dtype == torch.float32), N, H, float(eps), _stream())
+    _cabi.check(rc, "bagel_rmsnorm_f32")
+    return out
+
+
+def latent_embed_add_f32(proj, t_emb, pos_table, pos_ids, seq, dst_rows):
+    """dtype mode B: seq32[dst_rows[i]] = fp32(bf16(proj[i] + t_emb) + pos_table32[pos_ids[i]])."""
+    M, H = proj.shape
+    _req(proj, torch.bfloat16, "proj"); _opt(t_emb, torch.bfloat16, "t_emb"); _req(pos_table, torch.float32, "pos_table")
+    _req(pos_ids, torch.int64, "pos_ids"); _req(seq, torch.float32, "seq"); _opt(dst_rows, torch.int32, "dst_rows")
+    assert pos_table.shape[-1] == H and seq.shape[-1] >= H and pos_ids.numel() >= M
+    assert (dst_rows.numel() >= M) if dst_rows is not None else (seq.shape[0] >= M)
+    rc = _cabi.lib().bagel_latent_embed_add_f32(_ptr(proj), proj.stride(0), _ptr(t_emb), _ptr(pos_table), pos_table.stride(0),
+                                                _ptr(pos_ids), _ptr(seq), seq.stride(0), _ptr(dst_rows), M, H, _stream())
+    _cabi.check(rc, "bagel_latent_embed_add_f32")
+
+
+def copy_rows_f32(src: torch.Tensor, dst: torch.Tensor, src_rows=None, dst_rows=None, M: Optional[int] = None):
+    """Row gather/scatter of fp32 rows through the bf16 copy kernel (a pure byte copy: each fp32 row is 2H bf16 lanes)."""
+    _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
+    return copy_rows(src.view(torch.bfloat16), dst.view(torch.bfloat16), src_rows, dst_rows, M)

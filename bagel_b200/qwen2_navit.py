@@ -6,8 +6,12 @@ attention they call :499-600, :757-831) with the same argument names and meaning
 fixed sequence of hand-written sm_100a kernels (bagel_b200.ops). There is no nn.Module / autograd here: weights
 are plain device tensors in fused layouts (QKV concatenated, gate/up interleaved for the SwiGLU epilogue).
 
-Numerics follow the reference's "mode A" (bf16 weights under autocast, app.py:111 + inferencer.py:233): bf16
-residual stream, fp32 accumulation inside every kernel, the reference's bf16 rounding points kept.
+Numerics: `dtype_mode="A"` (default) follows the reference with bf16 weights under autocast (app.py:111 +
+inferencer.py:233): bf16 residual stream, fp32 accumulation inside every kernel, the reference's bf16 rounding points
+kept. `dtype_mode="B"` follows the reference with fp32 master weights under autocast (the eval drivers,
+eval/gen/gen_images_mp.py:159-175 + :73; SURVEY.md §8a dtype table): fp32 residual stream, fp32 RMSNorm weights and
+outputs, unrounded fp32 RoPE tables, fp32 q/k-norm arithmetic — every nn.Linear still runs bf16 x bf16 -> bf16 (GEMM
+weights are the fp32 checkpoint values cast to bf16 once at load, which is what autocast does on every call).
 
 MoT routing (reference: ~20 index gathers/scatters per layer, qwen2_navit.py:526-548, 593-594, 781-787,
 808-819): every row runs through the gen-expert GEMM; the few text rows (2 per image while denoising) are
@@ -50,15 +54,16 @@ class BaseNavitOutputWithPast:
 
 
 class _Embedding:
-    """model.embed_tokens: callable like nn.Embedding, gather done by bagel_copy_rows_bf16."""
+    """model.embed_tokens: callable like nn.Embedding, gather done by bagel_copy_rows_bf16 (table bf16, or fp32 in
+    dtype mode B — the rows are then copied as raw bytes)."""
 
     def __init__(self, weight: torch.Tensor):
         self.weight = weight
 
     def __call__(self, ids: torch.Tensor) -> torch.Tensor:
         ids32 = ids.to(device=self.weight.device, dtype=torch.int32)
-        out = torch.empty((ids32.numel(), self.weight.shape[1]), dtype=BF16, device=self.weight.device)
-        ops.copy_rows(self.weight, out, src_rows=ids32)
+        out = torch.empty((ids32.numel(), self.weight.shape[1]), dtype=self.weight.dtype, device=self.weight.device)
+        (ops.copy_rows_f32 if self.weight.dtype == torch.float32 else ops.copy_rows)(self.weight, out, src_rows=ids32)
         return out
 
 
@@ -114,7 +119,7 @@ class ForwardPlan:
         self.mode = mode
         # q/k-norm + RoPE arithmetic in fp32 only in PackedAttentionMoT's gen branch (qwen2_navit.py:542-548); the dense
         # PackedAttention every other layer class uses is the bf16 flow whatever the mode (:325-336)
-        self.fp32_flow = (mode == "gen") and lm.layer_kind == "mot"
+        self.fp32_flow = int((mode == "gen") and lm.layer_kind == "mot") + (2 if lm.dtype_mode == "B" else 0)
         self.q_rows = torch.as_tensor(packed_query_indexes).to(dev, torch.int32).contiguous()
         if self.n_ctx:
             self.ctx_rows = torch.as_tensor(packed_key_value_indexes).to(dev, torch.int32).contiguous()
@@ -131,16 +136,20 @@ class ForwardPlan:
             self.text_rows = ti.to(dev, torch.int32).contiguous() if ti.numel() else None
         pos = torch.as_tensor(position_ids).to(dev, torch.int64).contiguous()
         assert pos.numel() == self.n, "one position id per packed query token"
-        # cos/sin take the dtype of the hidden stream (bf16 in mode A): modeling_qwen2.py:150
-        self.cos, self.sin = ops.rope_table(pos, lm.inv_freq, round_bf16=True)
+        # cos/sin take the dtype of the hidden stream (bf16 in mode A, fp32 in mode B): modeling_qwen2.py:150
+        self.cos, self.sin = ops.rope_table(pos, lm.inv_freq, round_bf16=(lm.dtype_mode == "A"))
 
 
 class Qwen2Model:
     """The decoder stack (reference Qwen2Model, qwen2_navit.py:943-1092)."""
 
-    def __init__(self, config: Qwen2Config, device="cuda"):
+    def __init__(self, config: Qwen2Config, device="cuda", dtype_mode: str = "A"):
         self.config = config
         self.device = torch.device(device)
+        if dtype_mode not in ("A", "B"):
+            raise ValueError("dtype_mode must be 'A' (bf16 weights + autocast) or 'B' (fp32 master weights + autocast)")
+        self.dtype_mode = dtype_mode
+        self.stream_dtype = torch.float32 if dtype_mode == "B" else BF16     # residual stream / norm weights / embeddings
         # decoder layer class (reference Decoder_layer_dict, qwen2_navit.py:936-940)
         kinds = {"Qwen2DecoderLayer": "dense", "Qwen2MoEDecoderLayer": "moe", "Qwen2MoTDecoderLayer": "mot"}
         if config.layer_module not in kinds:
@@ -160,11 +169,11 @@ class Qwen2Model:
         self._ws_gen = 0   # bumped on every workspace (re)allocation: CUDA graphs captured over older buffers are stale
 
     # ----------------------------------------------------------------------------------------------
-    def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
+    def _buf(self, name: str, rows: int, cols: int, dtype=BF16) -> torch.Tensor:
         """Grow-only activation workspace (no allocation inside the layer loop once warmed up)."""
         t = self._ws.get(name)
-        if t is None or t.shape[0] < rows or t.shape[1] != cols:
-            t = torch.empty((rows, cols), dtype=BF16, device=self.device)
+        if t is None or t.shape[0] < rows or t.shape[1] != cols or t.dtype != dtype:
+            t = torch.empty((rows, cols), dtype=dtype, device=self.device)
             self._ws[name] = t
             self._ws_gen += 1
         return t[:rows]
@@ -175,8 +184,9 @@ class Qwen2Model:
         cfg = self.config
         H, D, I = cfg.hidden_size, cfg.head_dim, cfg.intermediate_size
         Hq, Hk = cfg.num_attention_heads, cfg.num_key_value_heads
-        for name, cols in (("xa", H), ("xb", H), ("h", H), ("out", H), ("qkv", (Hq + 2 * Hk) * D), ("q", Hq * D),
-                           ("att", Hq * D), ("act", I)):
+        for name in ("xa", "xb"):
+            self._buf(name, rows, H, self.stream_dtype)
+        for name, cols in (("h", H), ("out", H), ("qkv", (Hq + 2 * Hk) * D), ("q", Hq * D), ("att", Hq * D), ("act", I)):
             self._buf(name, rows, cols)
         if text_rows:
             for name, cols in (("h_text", H), ("att_text", Hq * D), ("act_text", I)):
@@ -225,8 +235,11 @@ class Qwen2Model:
         a_expert = plan.expert if a_routed else None
         nta = nt if a_routed else 0
 
-        xa = self._buf("xa", n, H)
-        xb = self._buf("xb", n, H)
+        modeB = self.dtype_mode == "B"
+        rmsnorm = ops.rmsnorm_f32 if modeB else ops.rmsnorm           # fp32 stream + fp32 weights -> bf16 GEMM input
+        EPI_R = ops.EPI_RESID_F32 if modeB else ops.EPI_RESID         # residual add in the stream's dtype
+        xa = self._buf("xa", n, H, self.stream_dtype)
+        xb = self._buf("xb", n, H, self.stream_dtype)
         h = self._buf("h", n, H)
         qkv = self._buf("qkv", n, (Hq + 2 * Hk) * D)
         q = self._buf("q", n, Hq * D)
@@ -244,7 +257,7 @@ class Qwen2Model:
             und = layer.und
             amain = layer.gen if a_routed else layer.und     # norm / attention weights every row runs through
             # ---- attention block ----
-            ops.rmsnorm(xa, und.ln_in, amain.ln_in if a_routed else None, a_expert, eps, out=h)
+            rmsnorm(xa, und.ln_in, amain.ln_in if a_routed else None, a_expert, eps, out=h)
             if self.fused_qkv and D == 128:
                 # QKV GEMM with q/k-norm + RoPE + KV placement in its epilogue (no [n, 4608] round trip)
                 ops.gemm_qkv_norm_rope(h, amain.wqkv, amain.bqkv, und.q_norm, und.k_norm,
@@ -265,30 +278,36 @@ class Qwen2Model:
                                  plan.q_rows, Hq, Hk, D, eps, plan.fp32_flow)
             ops.attn_varlen(q.view(n, Hq, D), kbuf[li].view(-1, Hk, D), vbuf[li].view(-1, Hk, D), plan.cu_q, plan.cu_k,
                             plan.max_q, plan.max_k, plan.is_causal, out=att.view(n, Hq, D))
-            ops.gemm(att, amain.wo, resid=xa, epilogue=ops.EPI_RESID, out=xb)
+            ops.gemm(att, amain.wo, resid=xa, epilogue=EPI_R, out=xb)
             if nta:
                 ops.copy_rows(att, at, src_rows=plan.text_rows)
-                ops.gemm(at, und.wo, resid=xa, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xb)
+                ops.gemm(at, und.wo, resid=xa, row_map=plan.text_rows, epilogue=EPI_R, out=xb)
             # ---- MLP block ----
-            ops.rmsnorm(xb, und.ln_post, amain.ln_post if a_routed else None, a_expert, eps, out=h)
+            rmsnorm(xb, und.ln_post, amain.ln_post if a_routed else None, a_expert, eps, out=h)
             ops.gemm(h, main.wgu, epilogue=ops.EPI_SWIGLU, out=act)
-            ops.gemm(act, main.wd, resid=xb, epilogue=ops.EPI_RESID, out=xa)
+            ops.gemm(act, main.wd, resid=xb, epilogue=EPI_R, out=xa)
             if nt:
                 ops.copy_rows(h, ht, src_rows=plan.text_rows)
                 ops.gemm(ht, und.wgu, epilogue=ops.EPI_SWIGLU, out=actt)
-                ops.gemm(actt, und.wd, resid=xb, row_map=plan.text_rows, epilogue=ops.EPI_RESID, out=xa)
+                ops.gemm(actt, und.wd, resid=xb, row_map=plan.text_rows, epilogue=EPI_R, out=xa)
 
         if not final_norm:
             return xa
         return self.final_norm(plan)
 
-    def final_norm(self, plan: ForwardPlan) -> torch.Tensor:
-        """Final (routed) RMSNorm of the hidden state left in the "xa" workspace (qwen2_navit.py:1075-1084)."""
+    def final_norm(self, plan: ForwardPlan, for_linear: bool = False) -> torch.Tensor:
+        """Final (routed) RMSNorm of the hidden state left in the "xa" workspace (qwen2_navit.py:1075-1084). Mode B: the
+        norm output is fp32 (what forward_inference returns); for_linear=True gives its bf16 cast, i.e. the operand the
+        next nn.Linear (llm2vae / lm_head) sees under autocast."""
         n, H = plan.n, self.config.hidden_size
         routed = plan.expert is not None
-        xa = self._buf("xa", n, H)
+        xa = self._buf("xa", n, H, self.stream_dtype)
+        w1 = self.norm_moe_gen if routed else None
+        if self.dtype_mode == "B":
+            out = self._buf("out", n, H) if for_linear else self._buf("out32", n, H, torch.float32)
+            return ops.rmsnorm_f32(xa, self.norm, w1, plan.expert, self.config.rms_norm_eps, out=out)
         out = self._buf("out", n, H)
-        ops.rmsnorm(xa, self.norm, self.norm_moe_gen if routed else None, plan.expert, self.config.rms_norm_eps, out=out)
+        ops.rmsnorm(xa, self.norm, w1, plan.expert, self.config.rms_norm_eps, out=out)
         return out
 
     # ----------------------------------------------------------------------------------------------
@@ -305,7 +324,7 @@ class Qwen2Model:
         plan = ForwardPlan(self, query_lens, packed_query_position_ids, packed_query_indexes,
                            key_values_lens if has_ctx else None, packed_key_value_indexes if has_ctx else None,
                            is_causal, mode, packed_vae_token_indexes, packed_text_indexes)
-        x = packed_query_sequence.to(self.device, BF16)
+        x = packed_query_sequence.to(self.device, self.stream_dtype)
         kbuf, vbuf = self.alloc_kv(plan)
         self.place_context(plan, past_key_values, kbuf, vbuf)
         out = self.run_layers(x, plan, kbuf, vbuf).clone()
@@ -322,9 +341,9 @@ class Qwen2Model:
 class Qwen2ForCausalLM:
     """Reference Qwen2ForCausalLM (qwen2_navit.py:1095-1188): `.model`, `.lm_head`, forward_inference(...)."""
 
-    def __init__(self, config: Qwen2Config, device="cuda"):
+    def __init__(self, config: Qwen2Config, device="cuda", dtype_mode: str = "A"):
         self.config = config
-        self.model = Qwen2Model(config, device)
+        self.model = Qwen2Model(config, device, dtype_mode)
         self.lm_head: Optional[_Linear] = None
         self.vocab_size = config.vocab_size
 
@@ -348,15 +367,17 @@ class Qwen2ForCausalLM:
         dev = self.model.device
         used = set()
 
-        def get(name, required=True):
+        sdt = self.model.stream_dtype     # fp32 in dtype mode B: norm weights / embeddings keep the checkpoint precision
+
+        def get(name, required=True, dtype=BF16):
             if name in sd:
                 used.add(name)
-                return sd[name].to(dev, BF16)
+                return sd[name].to(dev, dtype)
             if required:
                 raise KeyError(f"missing weight {name}")
             return None
 
-        self.model.embed_tokens = _Embedding(get("model.embed_tokens.weight").contiguous())
+        self.model.embed_tokens = _Embedding(get("model.embed_tokens.weight", dtype=sdt).contiguous())
         for li, layer in enumerate(self.model.layers):
             p = f"model.layers.{li}."
             for sfx, tgt in (("", "und"), ("_moe_gen", "gen")):
@@ -380,8 +401,8 @@ class Qwen2ForCausalLM:
                                     get(a + f"v_proj{sfx}.bias")], dim=0).contiguous()
                 e.wo = get(a + f"o_proj{sfx}.weight").contiguous()
                 if cfg.qk_norm:
-                    e.q_norm = get(a + f"q_norm{sfx}.weight").contiguous()
-                    e.k_norm = get(a + f"k_norm{sfx}.weight").contiguous()
+                    e.q_norm = get(a + f"q_norm{sfx}.weight", dtype=sdt).contiguous()
+                    e.k_norm = get(a + f"k_norm{sfx}.weight", dtype=sdt).contiguous()
                 else:
                     # nn.Identity in the reference (:247-252, :398-404); no shipped BAGEL config uses it and the fused
                     # QKV epilogue has no norm-free variant, so say so at load time instead of mis-computing later
@@ -390,15 +411,15 @@ class Qwen2ForCausalLM:
                 m = p + f"mlp{sfx}."
                 e.wgu = ops.interleave_gate_up(get(m + "gate_proj.weight"), get(m + "up_proj.weight"))
                 e.wd = get(m + "down_proj.weight").contiguous()
-                e.ln_in = get(p + f"input_layernorm{sfx}.weight").contiguous()
-                e.ln_post = get(p + f"post_attention_layernorm{sfx}.weight").contiguous()
+                e.ln_in = get(p + f"input_layernorm{sfx}.weight", dtype=sdt).contiguous()
+                e.ln_post = get(p + f"post_attention_layernorm{sfx}.weight", dtype=sdt).contiguous()
                 setattr(layer, tgt, e)
-        self.model.norm = get("model.norm.weight").contiguous()
+        self.model.norm = get("model.norm.weight", dtype=sdt).contiguous()
         if self.model.use_moe:
-            self.model.norm_moe_gen = get("model.norm_moe_gen.weight").contiguous()
+            self.model.norm_moe_gen = get("model.norm_moe_gen.weight", dtype=sdt).contiguous()
         lw = get("lm_head.weight", required=False)
         if lw is None and cfg.tie_word_embeddings:
-            lw = self.model.embed_tokens.weight
+            lw = self.model.embed_tokens.weight.to(BF16)
         self.lm_head = _Linear(lw.contiguous()) if lw is not None else None
         unexpected = [k for k in sd if k not in used]
         if strict and unexpected:

@@ -43,6 +43,8 @@ long long bagel_launch_count(void);
 #define BAGEL_EPI_GELU 3   /* C = bf16(gelu_tanh(bf16(acc + bias)))                  SiglipMLP / connector   */
 #define BAGEL_EPI_SILU 4   /* C = bf16(silu(bf16(acc + bias)))                       TimestepEmbedder.mlp[0:2] */
 #define BAGEL_EPI_F32 5    /* C (fp32 [M, ldc]) = acc + bias                         attention logits, VAE mid block */
+#define BAGEL_EPI_RESID_F32 7 /* C (fp32) = resid (fp32 [*, ldr]) + bf16(acc + bias)    fp32 residual stream: dtype mode B
+                              * (fp32 master weights under autocast, eval/gen/gen_images_mp.py:159-175, :73)            */
 
 /* C[M,N] = epilogue(A[M,K] @ W[N,K]^T), bf16 in / fp32 accumulate (tcgen05, TMEM) / bf16 out.
  * Replaces nn.Linear at modeling/bagel/qwen2_navit.py:515-517,529-536 (q/k/v_proj{,_moe_gen}),
@@ -112,7 +114,12 @@ int bagel_rope_table(const long long* pos, const float* inv_freq, float* cos_t, 
  * (PackedAttentionMoT.forward_inference, modeling/bagel/qwen2_navit.py:518-519, 542-557, 559-574).
  *   qkv [N, (Hq+2Hk)*D] bf16; q_out [N, Hq*D]; k_out / v_out [rows, Hk*D] written at row kv_rows[r] (NULL: r);
  *   *_w0 und-expert norm weights [D], *_w1 gen-expert (NULL when not MoT), expert[N] routing flags (may be NULL);
- *   fp32_flow: 1 = mode "gen" numerics (fp32 norm+RoPE, single bf16 cast), 0 = mode "und" (bf16 at every op). */
+ *   fp32_flow: rounding-point flow of the reference (SURVEY.md 8a dtype table):
+ *     0 = bf16 weights, und / dense attention (bf16 at every op, bf16-rounded cos/sin);
+ *     1 = bf16 weights, MoT gen branch (fp32 norm + RoPE, single bf16 cast);
+ *     2 = fp32 master weights, und / dense (bf16(x*r) * w_fp32, fp32 RoPE with fp32 cos/sin);
+ *     3 = fp32 master weights, MoT gen branch (everything fp32).
+ *   flows 2 and 3 read q_w* / k_w* as FP32 [D] (bagel_gemm_qkv_norm_rope takes the same values). */
 int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void* q_w0, const void* k_w0, const void* q_w1,
                        const void* k_w1, const uint8_t* expert, const float* cos_t, const float* sin_t, void* q_out,
                        long long ld_q, void* k_out, void* v_out, long long ld_kv, const int* kv_rows, int N, int Hq,
@@ -204,6 +211,19 @@ int bagel_taylor_eval_bf16(const void* factors, long long plane_stride, int n_fa
 int bagel_siglip_rope2d_bf16(void* x, long long ld, int n_tokens, int heads, int head_stride, int head_dim,
                              const long long* pos_ids, const float* cos_h, const float* sin_h, const float* cos_w,
                              const float* sin_w, void* stream);
+
+/* dtype mode B (fp32 master weights + autocast): RMSNorm of an FP32 hidden stream with FP32 weights,
+ * y = w_e * (x * rsqrt(mean(x^2) + eps)) with both products rounded to fp32 (modeling/qwen2/modeling_qwen2.py:54-59);
+ * out_f32 = 1 stores that fp32 value (the final norm handed back to the caller), 0 stores bf16(y) — the autocast cast
+ * in front of the next nn.Linear. Routing by expert[row] as bagel_rmsnorm_bf16. */
+int bagel_rmsnorm_f32(const float* x, long long ldx, const float* w0, const float* w1, const uint8_t* expert, void* y,
+                      long long ldy, int out_f32, int N, int H, float eps, void* stream);
+
+/* bagel_latent_embed_add for an fp32 hidden stream: seq32[dst_rows[i]] = fp32(bf16(proj[i] + t_emb) + pos_table32[pos_ids[i]])
+ * (modeling/bagel/bagel.py:801-806 with fp32 parameters: the frozen sincos table and the packed sequence are fp32). */
+int bagel_latent_embed_add_f32(const void* proj, long long ldp, const void* t_emb, const float* pos_table, long long ldt,
+                               const long long* pos_ids, float* seq, long long lds, const int* dst_rows, int M, int H,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -509,6 +509,108 @@ def golden_lm_variants(ns):
     save_file(out, os.path.join(OUT, "lm_variants.safetensors"))
 
 
+def golden_mode_b(ns):
+    """dtype mode B — fp32 master weights under autocast, the way the eval drivers load the model
+    (eval/gen/gen_images_mp.py:159-175, autocast :73): fp32 residual stream / norm outputs / RoPE tables.
+    LM forward at head_dim 128 (lm_config1.safetensors already holds d64.B), and the text prefill + generate_image flow
+    for both head dims."""
+    out = {}
+    dtype = torch.float32
+    # ---- LM forward, d128 ----
+    cfg = fixtures.TINY128_LM
+    sd = fixtures.lm_state_dict(cfg, seed=0, dtype=dtype)
+    lm, _ = ref_lm(ns, cfg, sd, dtype)
+    inp = fixtures.config1_inputs(cfg, dtype=dtype)
+    n = 130
+    xg = torch.randn(n, cfg.hidden_size, generator=torch.Generator().manual_seed(5)).to(dtype)
+    kw = dict(query_lens=torch.tensor([n], dtype=torch.int32), packed_query_position_ids=torch.full((n,), 512, dtype=torch.long),
+              packed_query_indexes=torch.arange(512, 512 + n), key_values_lens=torch.tensor([512], dtype=torch.int32),
+              packed_key_value_indexes=torch.arange(512), update_past_key_values=False, is_causal=False, mode="gen",
+              packed_vae_token_indexes=torch.arange(1, n - 1), packed_text_indexes=torch.tensor([0, n - 1]))
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        cache = ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers)
+        und = lm.forward_inference(
+            packed_query_sequence=inp["x"], query_lens=inp["query_lens"], packed_query_position_ids=inp["und_position_ids"],
+            packed_query_indexes=inp["query_indexes"], past_key_values=cache, key_values_lens=torch.tensor([0], dtype=torch.int32),
+            packed_key_value_indexes=torch.zeros(0, dtype=torch.long), update_past_key_values=True, is_causal=True, mode="und")
+        gen = lm.forward_inference(packed_query_sequence=xg, past_key_values=cache, **kw)
+    with torch.no_grad():
+        oc = om.KVCache(cfg.num_hidden_layers)
+        oh, oc = om.lm_forward_inference(sd, cfg, inp["x"], inp["query_lens"], inp["und_position_ids"], inp["query_indexes"],
+                                         oc, torch.tensor([0], dtype=torch.int32), torch.zeros(0, dtype=torch.long), True, True, "und")
+        og, _ = om.lm_forward_inference(sd, cfg, xg, past_key_values=oc, **kw)
+    assert torch.equal(oh, und.packed_query_sequence) and torch.equal(og, gen.packed_query_sequence), "oracle != reference (d128 B)"
+    assert und.packed_query_sequence.dtype == torch.float32
+    out["d128.B.und_hidden"] = und.packed_query_sequence.contiguous()
+    out["d128.B.gen_hidden"] = gen.packed_query_sequence.contiguous()
+    out["d128.B.k_cache_last"] = cache.key_cache[cfg.num_hidden_layers - 1].contiguous()
+    out["d128.B.v_cache_last"] = cache.value_cache[cfg.num_hidden_layers - 1].contiguous()
+    print("mode B lm forward d128: oracle == reference (bit-exact)")
+    # ---- flow ----
+    tok = IntTokenizer()
+    prompts = ["5 17 900 33 2", "8 8 100 4 77 650 12"]
+    prompt_ids = [tok.encode(p) for p in prompts]
+    image_sizes = [(64, 64), (64, 96)]
+    for tag, cfg in (("d64", fixtures.TINY_LM), ("d128", fixtures.TINY128_LM)):
+        sd = flow_state_dict(cfg, dtype)
+        model = build_ref_bagel(ns, cfg, sd, dtype)
+        sd_full = dict(sd)
+        sd_full["latent_pos_embed.pos_embed"] = model.latent_pos_embed.pos_embed.data.clone()
+        assert sd_full["latent_pos_embed.pos_embed"].dtype == torch.float32
+        fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+
+        def ctx(with_text):
+            rc, oc_ = ns.qwen2_navit.NaiveCache(cfg.num_hidden_layers), om.KVCache(cfg.num_hidden_layers)
+            kv, rp = [0, 0], [0, 0]
+            if with_text:
+                gi_, kv, rp = model.prepare_prompts(kv, rp, prompts, tok, NEW_TOKEN_IDS)
+                ogi_, _, _ = obf.prepare_prompts([0, 0], [0, 0], prompt_ids, NEW_TOKEN_IDS["bos_token_id"], NEW_TOKEN_IDS["eos_token_id"])
+                with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                    rc = model.forward_cache_update_text(rc, **gi_)
+                with torch.no_grad():
+                    oc_ = obf.forward_cache_update_text(sd_full, fc, oc_, **ogi_)
+                for li in range(cfg.num_hidden_layers):
+                    assert torch.equal(rc.key_cache[li], oc_.key_cache[li])
+            return rc, oc_, kv, rp
+
+        rc_main, oc_main, kv_main, rp_main = ctx(True)
+        rc_txt, oc_txt, kv_txt, rp_txt = ctx(False)
+        rc_img, oc_img, kv_img, rp_img = ctx(True)
+        out[f"{tag}.prefill.k_cache_last"] = rc_main.key_cache[cfg.num_hidden_layers - 1].contiguous()
+        torch.manual_seed(2)
+        gi = model.prepare_vae_latent(kv_main, rp_main, image_sizes, NEW_TOKEN_IDS)
+        cfg_t = model.prepare_vae_latent_cfg(kv_txt, rp_txt, image_sizes)
+        cfg_i = model.prepare_vae_latent_cfg(kv_img, rp_img, image_sizes)
+
+        def obranch(d, cache):
+            return dict(packed_position_ids=d["cfg_packed_position_ids"], packed_query_indexes=d["cfg_packed_query_indexes"],
+                        key_values_lens=d["cfg_key_values_lens"], past_key_values=cache,
+                        packed_key_value_indexes=d["cfg_packed_key_value_indexes"])
+
+        for name, sT, sI, rt in [("nocfg", 1.0, 1.0, "global"), ("global_img", 4.0, 1.5, "global"),
+                                 ("text_channel_img", 4.0, 1.5, "text_channel")]:
+            kwargs = dict(num_timesteps=4, timestep_shift=3.0, cfg_renorm_min=0.0, cfg_renorm_type=rt, cfg_interval=[0.4, 1.0],
+                          cfg_text_scale=sT, cfg_img_scale=sI)
+            ref_kw = dict(kwargs)
+            ref_kw.update(
+                cfg_text_packed_position_ids=cfg_t["cfg_packed_position_ids"], cfg_text_packed_query_indexes=cfg_t["cfg_packed_query_indexes"],
+                cfg_text_key_values_lens=cfg_t["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=cfg_t["cfg_packed_key_value_indexes"],
+                cfg_text_past_key_values=rc_txt,
+                cfg_img_packed_position_ids=cfg_i["cfg_packed_position_ids"], cfg_img_packed_query_indexes=cfg_i["cfg_packed_query_indexes"],
+                cfg_img_key_values_lens=cfg_i["cfg_key_values_lens"], cfg_img_packed_key_value_indexes=cfg_i["cfg_packed_key_value_indexes"],
+                cfg_img_past_key_values=rc_img)
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                lat = model.generate_image(past_key_values=rc_main, **gi, **ref_kw)
+            with torch.no_grad():
+                olat = obf.generate_image(sd_full, fc, dict(gi), oc_main, cfg_text=obranch(cfg_t, oc_txt),
+                                          cfg_img=obranch(cfg_i, oc_img), **kwargs)
+            for a, b in zip(lat, olat):
+                assert torch.equal(a, b), f"oracle generate_image != reference (mode B {tag} {name})"
+            out[f"{tag}.gen.{name}.latents"] = torch.cat(lat, dim=0).contiguous()
+            print(f"mode B generate_image[{tag} {name}]: oracle == reference (bit-exact)")
+    save_file(out, os.path.join(OUT, "mode_b_tiny.safetensors"))
+
+
 def _ref_bagel_with_vit(ns, rope):
     cfg = fixtures.TINY_LM
     dtype = torch.bfloat16
@@ -588,6 +690,7 @@ def main():
         golden_lm_variants(ns)
         golden_vit_rope(ns)
         golden_chat(ns)
+        golden_mode_b(ns)
         return
     golden_lm_config1(ns)
     golden_flow(ns)
@@ -597,6 +700,7 @@ def main():
     golden_lm_variants(ns)
     golden_vit_rope(ns)
     golden_chat(ns)
+    golden_mode_b(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

@@ -32,8 +32,10 @@ def tiny_vae(device="cuda"):
     return ae
 
 
-def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, load=True, vae_downsample=8):
-    """bagel_b200.Bagel for the tiny config (device='cpu' only exercises host logic: packers, config)."""
+def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, load=True, vae_downsample=8,
+                        dtype_mode="A"):
+    """bagel_b200.Bagel for the tiny config (device='cpu' only exercises host logic: packers, config).
+    dtype_mode "B": fp32 master weights (the state dict is then generated in fp32)."""
     from bagel_b200.bagel import Bagel
     from bagel_b200.config import AutoEncoderParams, BagelConfig, Qwen2Config
     from bagel_b200.qwen2_navit import Qwen2ForCausalLM
@@ -45,10 +47,11 @@ def build_product_bagel(cfg=fixtures.TINY_LM, device="cuda", max_latent_size=8, 
     bcfg = BagelConfig(visual_gen=True, visual_und=False, llm_config=llm, vit_config=None,
                        vae_config=AutoEncoderParams(downsample=vae_downsample), latent_patch_size=2,
                        max_latent_size=max_latent_size)
-    lm = Qwen2ForCausalLM(llm, device=device)
+    lm = Qwen2ForCausalLM(llm, device=device, dtype_mode=dtype_mode)
     model = Bagel(lm, None, bcfg)
     if load:
-        model.load_state_dict(flow_state_dict(cfg, max_latent_size=max_latent_size))
+        model.load_state_dict(flow_state_dict(cfg, torch.float32 if dtype_mode == "B" else torch.bfloat16,
+                                              max_latent_size=max_latent_size))
     return model
 
 
