@@ -594,8 +594,11 @@ class Bagel:
         total = int(cap.sum())
         max_kv = int(cap.max())   # host upper bound of any sample's key count (sizes the key split of decode attention)
         has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None and int(kv.sum()) > 0
-        kbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
-        vbuf = torch.empty((L, total, w), dtype=BF16, device=dev)
+        # zero-filled, not torch.empty: attention multiplies the masked probabilities (exactly 0) with whatever sits in the
+        # spare rows of a slab — 0 x NaN/Inf garbage would poison the output (the tcgen05 kernel fetches whole 128-key
+        # blocks by TMA; only the single-query d=128 kernel clamps its loads to the rows in use)
+        kbuf = torch.zeros((L, total, w), dtype=BF16, device=dev)
+        vbuf = torch.zeros((L, total, w), dtype=BF16, device=dev)
         if has_ctx:
             n_ctx = int(kv.sum())
             dst = _ranges(begin, kv).to(dev, torch.int32)

@@ -5,19 +5,18 @@
 //   out[Sq,Hq,D] = softmax(q k^T * scale [+ bottom-right causal mask]) v   per packed sample, GQA by Hq % Hk == 0,
 //   bf16 in / fp32 softmax + accumulation / bf16 out.
 //
-// One CTA owns TWO 128-row query tiles of one (sample, head) and sweeps the keys in blocks of 128. With kSplit
-// threads per score row (1 or 2; W = 4*kSplit warps per tile):
-//   warps [0, W)      softmax group of tile 0: tcgen05.ld S -> online softmax -> P (bf16) back into the S columns of
-//   warps [W, 2W)     softmax group of tile 1  TMEM; rescales O in TMEM when the running max jumps; final O / l -> global.
-//                     kSplit = 2: warps w and w+4 of a group share the same 32 rows (same TMEM lane quarter) and take
-//                     the left / right half of the columns; they agree on the row maximum through shared memory and a
-//                     64-thread named barrier per block. The softmax of one tile is a serial stage between its two MMAs
-//                     (S -> P -> PV) of ~2400 cycles; kSplit = 2 was built to test whether that is an instruction-issue
-//                     limit — it is not (slower, see the launch code), so kSplit = 1 is the default.
-//   warp 2W           TMA producer: Q tiles once, then K_j / V_j blocks through a kStages smem ring
-//   warp 2W+1         MMA issuer (one lane): S_t = Q_t K_j^T  (SS, both K-major)  and  O_t += P_t V_j (TS: A = P in TMEM,
-//                     B = V MN-major) — the tensor pipe runs tile 0 while tile 1 is in softmax and vice versa
+// PERSISTENT kernel, one CTA per SM. A work item = TWO 128-row query tiles of one (sample, head), swept over that sample's
+// keys in blocks of 128; items are handed out by a device-side counter (dynamic scheduling):
+//   warps 0-3 / 4-7   softmax group of tile 0 / tile 1: tcgen05.ld S -> online softmax -> P (bf16) back into the S columns of
+//                     TMEM; rescales O in TMEM when the running max jumps; final O / l -> global
+//   warp 8            scheduler + TMA producer: fetches the next item (atomicAdd, published through shared memory), loads its
+//                     Q tiles (as soon as the previous item's last QK^T has read Q), then K_j / V_j through a smem ring
+//   warp 9            MMA issuer (one lane): S_t = Q_t K_j^T  (SS, both K-major)  and  O_t += P_t V_j (TS: A = P in TMEM,
+//                     B = V MN-major) — the tensor pipe runs tile 0 while tile 1 is in softmax and vice versa; the first
+//                     QK^T of the next item is issued while the softmax warps still write out the current item's O
 // TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D); P_t aliases S_t columns [0,64).
+// (Round 1's one-CTA-per-item grid paid launch + TMEM allocation + barrier set-up + pipeline ramp per item: ~4 key blocks
+// worth of time, i.e. 33 % at L = 1k. Its "two threads per score row" variant was measured slower and is gone.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -25,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -33,8 +33,8 @@
 
 namespace bagel {
 
-constexpr int attn_threads(int split) { return (8 * split + 2) * 32; }  // softmax warps of both tiles + TMA + MMA
-constexpr int kBlockM = 128;  // rows per query tile (2 tiles per CTA)
+constexpr int kAttnThreads = (8 + 2) * 32;  // softmax warps of both tiles (4 + 4) + TMA warp + MMA warp
+constexpr int kBlockM = 128;  // rows per query tile (2 tiles per work item)
 constexpr int kBlockN = 128;  // keys per block
 
 struct AttnParams {
@@ -46,14 +46,16 @@ struct AttnParams {
   int Hq, Hk;
   int causal;
   float scale_log2;  // softmax_scale * log2(e)
+  int qtiles;        // work items per (sample, head): ceil(max_seqlen_q / 256)
+  int num_items;     // qtiles * Hq * batch
+  int* sched;        // device counter (zeroed before the launch): next work item to hand out
 };
 
 template <int D>
 struct AttnCfg {
   static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
   static constexpr int kStages = (D == 128) ? 4 : 6;
-  static constexpr int kXchgBytes = 2 * 2 * 2 * 2 * kBlockM * 4;  // [kind][parity][tile][half][row] fp32 exchange of row sums / maxima (kSplit = 2)
-  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 256 + kXchgBytes;
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512;
 };
 
 // packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of FMA / ADD
@@ -79,12 +81,49 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// One unit of work: two 128-row query tiles of one (sample, head) against that sample's keys.
+struct AttnItem {
+  int b, h, hk;
+  int q_beg, Lq, k_beg, Lk;
+  int q0;            // first query row (within the sample)
+  int shift;         // bottom-right aligned causal: key kv visible to query qi iff kv <= qi + shift
+  int nblk;          // key blocks to sweep
+  bool valid;        // q0 < Lq
+  bool tile1_active;
+};
+
+__device__ __forceinline__ AttnItem attn_decode_item(int item, const AttnParams& p) {
+  AttnItem w;
+  // q tiles of one (sample, head) are consecutive items: the CTAs running at any moment share those K/V blocks through the
+  // L2. Causal: the LAST query tiles sweep the most keys — hand them out first (longest-processing-time-first).
+  const int qi = item % p.qtiles;
+  const int bh = item / p.qtiles;
+  w.h = bh % p.Hq;
+  w.b = bh / p.Hq;
+  w.hk = w.h / (p.Hq / p.Hk);
+  const int qt = p.causal ? (p.qtiles - 1 - qi) : qi;
+  w.q_beg = p.cu_q[w.b];
+  w.Lq = p.cu_q[w.b + 1] - w.q_beg;
+  w.k_beg = p.cu_k[w.b];
+  w.Lk = p.seqused_k ? p.seqused_k[w.b] : (p.cu_k[w.b + 1] - w.k_beg);
+  w.q0 = qt * 2 * kBlockM;
+  w.valid = w.q0 < w.Lq;
+  w.tile1_active = (w.q0 + kBlockM) < w.Lq;
+  w.shift = w.Lk - w.Lq;
+  int kv_end = w.Lk;
+  if (p.causal) {
+    const int q_hi = min(w.Lq, w.q0 + 2 * kBlockM) - 1;
+    kv_end = max(0, min(w.Lk, q_hi + w.shift + 1));
+  }
+  w.nblk = w.valid ? (kv_end + kBlockN - 1) / kBlockN : 0;
+  return w;
 }
 
-template <int D, int kSplit>  // kSplit: threads per score row (1: 8 softmax warps, 2: 16 softmax warps)
-__global__ void __launch_bounds__(attn_threads(kSplit), 1)
+// PERSISTENT kernel: one CTA per SM loops over work items handed out by a device-side counter (dynamic scheduling: ragged
+// and causal batches balance themselves; launch, TMEM allocation, barrier set-up and the pipeline ramp are paid once per
+// SM instead of once per item, and the Q load / first QK^T of the next item overlap the epilogue of the current one).
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Cfg = AttnCfg<D>;
@@ -92,40 +131,26 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int kTileBytes = Cfg::kTileBytes;
   constexpr int kAtoms = D / 64;               // 64-column (128 B) swizzle atoms per row
   constexpr int kAtomBytes = kBlockM * 128;    // one [128 rows x 64 cols] box
-
-  const int b = blockIdx.z;
-  const int h = blockIdx.y;
-  const int q_beg = p.cu_q[b], Lq = p.cu_q[b + 1] - q_beg;
-  const int k_beg = p.cu_k[b], Lk = p.seqused_k ? p.seqused_k[b] : (p.cu_k[b + 1] - k_beg);
-  const int q0 = blockIdx.x * 2 * kBlockM;  // first query row (within the sample) of this CTA
-  if (q0 >= Lq) return;                     // whole CTA idle (grid is sized by max_seqlen_q)
-  const bool tile1_active = (q0 + kBlockM) < Lq;
-  const int hk = h / (p.Hq / p.Hk);
-  const int shift = Lk - Lq;  // bottom-right aligned causal: key kv visible to query qi iff kv <= qi + shift
-
-  // number of key blocks this CTA sweeps
-  int kv_end = Lk;
-  if (p.causal) {
-    const int q_hi = min(Lq, q0 + 2 * kBlockM) - 1;
-    kv_end = max(0, min(Lk, q_hi + shift + 1));
-  }
-  const int nblk = (kv_end + kBlockN - 1) / kBlockN;
+  constexpr int kSoftWarps = 4;                // softmax warps per tile
+  constexpr int kTmaWarp = 2 * kSoftWarps, kMmaWarp = 2 * kSoftWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                      // 2 tiles
   uint8_t* smem_kv = smem + 2 * kTileBytes;    // ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kStages * kTileBytes);
-  uint64_t* q_bar = bars;                  // [1]
-  uint64_t* kv_full = bars + 1;            // [kStages]
+  uint64_t* q_full = bars;                 // [1]  TMA -> MMA: Q tiles of the item landed
+  uint64_t* q_empty = bars + 1;            // [1]  MMA -> TMA: last QK^T of the item has read Q
+  uint64_t* kv_full = bars + 2;            // [kStages]
   uint64_t* kv_empty = kv_full + kStages;  // [kStages]
   uint64_t* s_bar = kv_empty + kStages;    // [2]  MMA -> softmax: S_t(j) ready
   uint64_t* p_bar = s_bar + 2;             // [2]  softmax -> MMA: P_t(j) written (and O_t rescaled)
-  uint64_t* o_bar = p_bar + 2;             // [2]  MMA -> softmax: final O_t ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
-  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][2][2][kBlockM]
-  constexpr int kSoftWarps = 4 * kSplit;          // softmax warps per tile
-  constexpr int kTmaWarp = 2 * kSoftWarps, kMmaWarp = 2 * kSoftWarps + 1;
+  uint64_t* o_bar = p_bar + 2;             // [2]  MMA -> softmax: final O_t of the item ready
+  uint64_t* o_free = o_bar + 2;            // [2]  softmax -> MMA: O_t read out, the next item may overwrite it
+  uint64_t* sched_full = o_free + 2;       // [2]  TMA warp -> everyone: next work item published
+  uint64_t* sched_empty = sched_full + 2;  // [2]  everyone -> TMA warp: slot consumed
+  volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + 2);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,7 +159,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_bar, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -143,6 +169,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&s_bar[t], 1);
       mbar_init(&p_bar[t], kSoftWarps);
       mbar_init(&o_bar[t], 1);
+      mbar_init(&o_free[t], kSoftWarps);
+      mbar_init(&sched_full[t], 1);
+      mbar_init(&sched_empty[t], 1 + 2 * kSoftWarps);   // MMA lane + one lane of every softmax warp
     }
     fence_mbar_init();
   }
@@ -155,36 +184,57 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
 
   if (warp == kTmaWarp) {
-    // =========================== TMA producer ===========================
-    if (lane == 0 && nblk > 0) {
-      const int ntile = tile1_active ? 2 : 1;
-      mbar_expect_tx(q_bar, ntile * kTileBytes);
-      for (int t = 0; t < ntile; ++t)
-        for (int a = 0; a < kAtoms; ++a)
-          tma_load_2d(smem_q + t * kTileBytes + a * kAtomBytes, &tmQ, q_bar, h * D + a * 64,
-                      q_beg + q0 + t * kBlockM, kEvictFirst);
+    // =========================== scheduler + TMA producer ===========================
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          mbar_expect_tx(&kv_full[stage], kTileBytes);
-          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+      uint32_t q_phase = 0;
+      int slot = 0;
+      uint32_t sphase = 0;
+      int next = atomicAdd(p.sched, 1);
+      while (true) {
+        const int item = next;
+        mbar_wait(&sched_empty[slot], sphase ^ 1);
+        sched_item[slot] = item;
+        mbar_arrive(&sched_full[slot]);
+        if (++slot == 2) { slot = 0; sphase ^= 1; }
+        if (item >= p.num_items) break;
+        next = atomicAdd(p.sched, 1);   // in flight while this item's loads are issued
+        const AttnItem w = attn_decode_item(item, p);
+        if (w.nblk == 0) continue;
+        const int ntile = w.tile1_active ? 2 : 1;
+        mbar_wait(q_empty, q_phase ^ 1);   // the previous item's last QK^T has read its Q tiles
+        q_phase ^= 1;
+        mbar_expect_tx(q_full, ntile * kTileBytes);
+        for (int t = 0; t < ntile; ++t)
           for (int a = 0; a < kAtoms; ++a)
-            tma_load_2d(smem_kv + stage * kTileBytes + a * kAtomBytes, tm, &kv_full[stage], hk * D + a * 64,
-                        k_beg + j * kBlockN, kEvictLast);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            tma_load_2d(smem_q + t * kTileBytes + a * kAtomBytes, &tmQ, q_full, w.h * D + a * 64,
+                        w.q_beg + w.q0 + t * kBlockM, kEvictFirst);
+        for (int j = 0; j < w.nblk; ++j) {
+          for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+            mbar_wait(&kv_empty[stage], phase ^ 1);
+            mbar_expect_tx(&kv_full[stage], kTileBytes);
+            const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+            for (int a = 0; a < kAtoms; ++a)
+              tma_load_2d(smem_kv + stage * kTileBytes + a * kAtomBytes, tm, &kv_full[stage], w.hk * D + a * 64,
+                          w.k_beg + j * kBlockN, kEvictLast);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && nblk > 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S[128,128] = Q[128,D] K[128,D]^T
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, D, 0, 1);        // O[128,D] += P[128,128] V[128,D]
-      const int ntile = tile1_active ? 2 : 1;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t q_phase = 0;
+      uint32_t pcnt[2] = {0, 0};    // P blocks consumed per tile (parity of p_bar)
+      uint32_t icnt[2] = {0, 0};    // items processed per tile (parity of o_free)
+      int slot = 0;
+      uint32_t sphase = 0;
 
       auto issue_qk = [&](int t, int kstage) {
         // K-major operands: D columns = kAtoms atoms of 64; 4 UMMA_K=16 steps per atom (+32 B each)
@@ -208,54 +258,83 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       };
 
-      mbar_wait(q_bar, 0);
-      // block 0 scores for both tiles
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
-      for (int t = 0; t < ntile; ++t) issue_qk(t, stage);
-      umma_commit(&kv_empty[stage]);  // K_0 slot free once both S(0) are done
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      while (true) {
+        mbar_wait(&sched_full[slot], sphase);
+        const int item = sched_item[slot];
+        mbar_arrive(&sched_empty[slot]);
+        if (++slot == 2) { slot = 0; sphase ^= 1; }
+        if (item >= p.num_items) break;
+        const AttnItem w = attn_decode_item(item, p);
+        if (w.nblk == 0) continue;
+        const int nblk = w.nblk;
+        const int ntile = w.tile1_active ? 2 : 1;
 
-      for (int j = 0; j < nblk; ++j) {
-        const int vstage = stage;
-        mbar_wait(&kv_full[vstage], phase);  // V_j
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-        const int kstage = stage;
-        const bool has_next = (j + 1) < nblk;
-        if (has_next) {
-          mbar_wait(&kv_full[kstage], phase);  // K_{j+1}
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
+        mbar_wait(q_full, q_phase);
+        q_phase ^= 1;
+        // block 0 scores for both tiles
+        mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
-        for (int t = 0; t < ntile; ++t) {
-          mbar_wait(&p_bar[t], j & 1);  // P_t(j) in TMEM, O_t rescaled
+        for (int t = 0; t < ntile; ++t) issue_qk(t, stage);
+        umma_commit(&kv_empty[stage]);  // K_0 slot free once both S(0) are done
+        if (nblk == 1) umma_commit(q_empty);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+
+        for (int j = 0; j < nblk; ++j) {
+          const int vstage = stage;
+          mbar_wait(&kv_full[vstage], phase);  // V_j
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          const int kstage = stage;
+          const bool has_next = (j + 1) < nblk;
+          if (has_next) {
+            mbar_wait(&kv_full[kstage], phase);  // K_{j+1}
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
           tc_fence_after();
-          issue_pv(t, vstage, j > 0);
-          if (!has_next) umma_commit(&o_bar[t]);
-          // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
-          if (has_next) issue_qk(t, kstage);
+          for (int t = 0; t < ntile; ++t) {
+            mbar_wait(&p_bar[t], pcnt[t] & 1);  // P_t(j) in TMEM, O_t rescaled
+            ++pcnt[t];
+            if (j == 0) mbar_wait(&o_free[t], (icnt[t] & 1) ^ 1);   // the previous item's O_t has been read out
+            tc_fence_after();
+            issue_pv(t, vstage, j > 0);
+            if (!has_next) umma_commit(&o_bar[t]);
+            // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
+            if (has_next) issue_qk(t, kstage);
+          }
+          umma_commit(&kv_empty[vstage]);
+          if (has_next) umma_commit(&kv_empty[kstage]);
+          if (has_next && j + 2 == nblk) umma_commit(q_empty);   // that was the item's last QK^T
         }
-        umma_commit(&kv_empty[vstage]);
-        if (has_next) umma_commit(&kv_empty[kstage]);
+        for (int t = 0; t < ntile; ++t) ++icnt[t];
       }
     }
-  } else if (warp < 2 * kSoftWarps) {
+  } else {
     // =========================== softmax / correction / epilogue ===========================
     const int t = warp / kSoftWarps;                 // which query tile this warp group serves
-    const int hf = (warp % kSoftWarps) >> 2;         // which share of the columns (0 when kSplit == 1)
     const int quarter = warp & 3;                    // TMEM lane quarter accessible to this warp
     const int row = quarter * 32 + lane;
-    const int qi = q0 + t * kBlockM + row;  // query index within the sample
-    const bool active = (t == 0) || tile1_active;
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    constexpr int NC = kBlockN / kSplit;             // score columns per thread
-    constexpr int DO = D / kSplit;                   // output columns per thread
-    const uint32_t tS = tmem_S[t] + lane_off + hf * NC;
-    const uint32_t tP = tmem_S[t] + lane_off + hf * (NC / 2);   // packed bf16 probabilities of these columns
-    const uint32_t tO = tmem_O[t] + lane_off + hf * DO;
-    const int pair_bar = 1 + t * 4 + quarter;        // named barrier shared by the kSplit warps of one row quarter
+    constexpr int NC = kBlockN;                      // score columns per thread
+    const uint32_t tS = tmem_S[t] + lane_off;
+    const uint32_t tP = tmem_S[t] + lane_off;        // packed bf16 probabilities over the first 64 columns of S
+    const uint32_t tO = tmem_O[t] + lane_off;
+    uint32_t scnt = 0;     // S blocks consumed by this tile (parity of s_bar)
+    uint32_t icnt = 0;     // items processed by this tile (parity of o_bar)
+    int slot = 0;
+    uint32_t sphase = 0;
 
-    if (active) {
+    while (true) {
+      mbar_wait(&sched_full[slot], sphase);
+      const int item = sched_item[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sched_empty[slot]);
+      if (++slot == 2) { slot = 0; sphase ^= 1; }
+      if (item >= p.num_items) break;
+      const AttnItem w = attn_decode_item(item, p);
+      if (!w.valid || (t == 1 && !w.tile1_active)) continue;
+      const int nblk = w.nblk;
+      const int Lq = w.Lq, Lk = w.Lk, shift = w.shift;
+      const int qi = w.q0 + t * kBlockM + row;  // query index within the sample
+
       float m = -INFINITY, l = 0.f;
       // Streamed online softmax. The stage is bound by instruction issue (one softmax warp of each tile per scheduler),
       // so the hot loop is pared down to 6 instructions per PAIR of scores (FFMA2 scale/shift, 2x MUFU.EX2, FADD2 row sum,
@@ -263,32 +342,18 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // in flight chunk c is exponentiated against the reference maximum `m` carried over from earlier blocks (lazy
       // rescaling). Only when a row has no reference yet, or the row sum shows that m has become badly stale, is the
       // block redone the classic way: exact block maximum, move m, rescale O and l, re-read S.
-      // With kSplit = 2 the threads of a row keep identical m (they exchange sums / maxima through shared memory) and
-      // separate partial row sums, merged once at the end.
       // Redo trigger of the streamed path: the block's row sum of p = 2^((s - m) scale). With an up-to-date m every p <= 1
       // and the sum is <= 128; a stale m only scales p, l and O by a common power of two, which fp32 (and bf16, same
       // exponent range) absorb without loss — so the maximum itself is NOT tracked in the hot loop (one FMNMX3 per pair
       // of elements saved) and the block is redone exactly only when the sum says some p left the comfortable range
-      // (or overflowed: inf / NaN fail the comparison too).
+      // (or overflowed: inf / NaN fail the comparison too). Exercised by tests/test_gpu_attn_adversarial.py.
       constexpr float kRedoSum = 1073741824.0f;   // 2^30
-      // kSplit = 2: combine a per-thread value over the shares of a row; the barrier also orders "every share has
-      // finished reading S" before the P stores that follow
-      auto row_exchange = [&](float x, int j, int kind, bool is_max) -> float {
-        if constexpr (kSplit == 1) {
-          return x;
-        } else {
-          float* slot = xchg + (((kind * 2 + (j & 1)) * 2 + t) * 2) * kBlockM;
-          slot[hf * kBlockM + row] = x;
-          named_bar_sync(pair_bar, 64);
-          const float y = slot[(hf ^ 1) * kBlockM + row];
-          return is_max ? fmaxf(x, y) : (x + y);
-        }
-      };
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&s_bar[t], j & 1);
+        mbar_wait(&s_bar[t], scnt & 1);
+        ++scnt;
         tc_fence_after();
-        const int kv0 = j * kBlockN + hf * NC;     // first key of this thread's columns
-        const int tile_q_lo = q0 + t * kBlockM;
+        const int kv0 = j * kBlockN;               // first key of this block
+        const int tile_q_lo = w.q0 + t * kBlockM;
         const bool need_mask = (j * kBlockN + kBlockN > Lk) || (p.causal && (j * kBlockN + kBlockN - 1 > tile_q_lo + shift));
         const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);  // last visible key for this row
 
@@ -338,10 +403,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           };
           if (need_mask) stream(std::true_type{});
           else stream(std::false_type{});
-          const float rs_row = row_exchange((rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y), j, 0, false);
+          const float rs_row = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
           redo = !(rs_row <= kRedoSum);
-        } else if constexpr (kSplit > 1) {
-          named_bar_sync(pair_bar, 64);    // keep the barrier count of the two shares equal on every path
         }
         float alpha = 1.0f;
         if (__any_sync(0xffffffffu, redo)) {
@@ -360,7 +423,6 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               mx = fmaxf(mx, x);
             }
           }
-          mx = row_exchange(mx, j, 1, true);     // exact block maximum of the row, identical in every share
           float neg_ms = -m * p.scale_log2;
           if (redo) {
             const float m_new = fmaxf(m, mx);
@@ -383,7 +445,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
 #pragma unroll
-            for (int c = 0; c < DO / 32; ++c) {
+            for (int c = 0; c < D / 32; ++c) {
               uint32_t v[32];
               tmem_ld_x32(tO + c * 32, v);
               tmem_ld_wait();
@@ -392,8 +454,6 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               tmem_st_x32(tO + c * 32, v);
             }
           }
-          // the other share re-read S too: its reads must be over before P lands on those columns
-          if constexpr (kSplit > 1) named_bar_sync(pair_bar, 64);
         }
         const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
@@ -408,19 +468,17 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
-      if constexpr (kSplit > 1) {   // total row sum = own share + the other share's (same m in both)
-        l = row_exchange(l, nblk, 0, false);
-      }
       if (nblk > 0) {
-        mbar_wait(&o_bar[t], 0);
+        mbar_wait(&o_bar[t], icnt & 1);
+        ++icnt;
         tc_fence_after();
       }
       // rows that never saw a visible key (m still -inf) produce 0, as flash-attn does
       const float inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;
       const bool row_ok = qi < Lq;
-      __nv_bfloat16* orow = p.out + (long long)(q_beg + qi) * p.ld_out + h * D + hf * DO;
+      __nv_bfloat16* orow = p.out + (long long)(w.q_beg + qi) * p.ld_out + w.h * D;
 #pragma unroll
-      for (int c = 0; c < DO / 32; ++c) {
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t v[32];
         if (nblk > 0) {
           tmem_ld_x32(tO + c * 32, v);
@@ -441,6 +499,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      if (nblk > 0) {   // O_t is in registers / memory: the next item's first P*V may overwrite the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
+      }
     }
   }
 
@@ -452,18 +515,43 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int D, int kSplit>
-static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p,
-                       int B, int max_seqlen_q, cudaStream_t stream) {
+// device counters of the work-item scheduler: a small ring so that back-to-back launches (and launches captured in a CUDA
+// graph together with their memset node) never share a counter that is still in use
+static int* sched_counter(cudaStream_t stream) {
+  constexpr int kRing = 64;
+  static int* base[64] = {nullptr};
+  static std::atomic<unsigned> next{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (base[dev] == nullptr) {
+    int* ptr = nullptr;
+    if (cudaMalloc(&ptr, kRing * sizeof(int)) != cudaSuccess) return nullptr;
+    base[dev] = ptr;
+  }
+  int* c = base[dev] + (next.fetch_add(1, std::memory_order_relaxed) % kRing);
+  if (cudaMemsetAsync(c, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
+  return c;
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, AttnParams p, int B,
+                       int max_seqlen_q, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  auto kern = attn_varlen_kernel<D, kSplit>;
+  auto kern = attn_varlen_kernel<D>;
   static bool attr_done = false;
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  dim3 grid((max_seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM), p.Hq, B);
-  kern<<<grid, attn_threads(kSplit), Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  p.qtiles = (max_seqlen_q + 2 * kBlockM - 1) / (2 * kBlockM);
+  const long long items = (long long)p.qtiles * p.Hq * B;
+  if (items > 0x7fffffff - 4096) return set_error(BAGEL_ERR_SHAPE, "bagel_attn_varlen_fwd: too many work items");
+  p.num_items = (int)items;
+  p.sched = sched_counter(stream);
+  if (p.sched == nullptr) return set_error(BAGEL_ERR_CUDA, "bagel_attn_varlen_fwd: scheduler counter allocation failed");
+  const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -510,13 +598,6 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // BAGEL_ATTN_SPLIT = threads per score row (default 1; 2 = 16 softmax warps). A/B knob: measured SLOWER on B200
-  // (denoise shape 801 vs 928 TFLOP/s, profiles/r01_attn_rowsplit_ab.txt) — the softmax stage of a tile is bound by
-  // the TMEM read/write port and the MUFU, which more warps do not widen, not by per-warp instruction issue.
-  static const int split = [] { const char* e = getenv("BAGEL_ATTN_SPLIT"); return e ? atoi(e) : 1; }();
-  if (head_dim == 128)
-    return split == 1 ? launch_attn<128, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
-                      : launch_attn<128, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
-  return split == 1 ? launch_attn<64, 1>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s)
-                    : launch_attn<64, 2>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  if (head_dim == 128) return launch_attn<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
+  return launch_attn<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
 }

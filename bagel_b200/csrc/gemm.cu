@@ -20,63 +20,10 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "gemm_skinny.h"
+#include "gemm_params.h"
+#include "gemm2.h"
 
 namespace bagel {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom along K
-constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
-
-enum GemmEpilogue : int {
-  EPI_BIAS = 0,    // C = bf16(acc + bias)
-  EPI_RESID = 1,   // C = bf16(resid + bf16(acc + bias))                (o_proj / down_proj + residual add)
-  EPI_SWIGLU = 2,  // C[:, j] = bf16(bf16(silu(bf16 g_j)) * bf16 u_j); W rows interleaved per 256 (128 g | 128 u)
-  EPI_GELU = 3,    // C = bf16(gelu_tanh(bf16(acc + bias)))             (SigLIP MLP / connector)
-  EPI_SILU = 4,    // C = bf16(silu(bf16(acc + bias)))                  (timestep MLP)
-  EPI_F32 = 5,     // C32 = acc (+ bias) as fp32                        (attention logits of the VAE mid block)
-  EPI_QKV = 6,     // fused q/k RMSNorm + RoPE + bf16 cast + K/V placement  (PackedAttentionMoT, head_dim 128)
-  EPI_RESID_F32 = 7,  // C32 = resid32 + bf16(acc + bias): fp32 residual stream of dtype mode B (fp32 master weights)
-};
-
-// Extra arguments of the fused QKV epilogue (see bagel_gemm_qkv_norm_rope in include/bagel_b200.h).
-struct QkvEpi {
-  const void *qw0, *kw0, *qw1, *kw1;  // per-head RMSNorm weights [128]: und / gen expert (may be null); bf16, fp32 for flow >= 2
-  const uint8_t* expert;                       // [rows] 1 = gen expert
-  const float *cos_t, *sin_t;                  // [rows, 64]
-  __nv_bfloat16 *q_out, *k_out, *v_out;
-  long long ld_q, ld_kv;
-  const int* kv_rows;                          // destination row of each token in the merged K/V buffers
-  int Hq, Hk;
-  float eps;
-  int fp32_flow;  // rounding-point flow 0..3, see qk_norm_rope_kernel in elementwise.cu
-};
-
-struct GemmParams {
-  int M, N, K;
-  __nv_bfloat16* C;
-  long long ldc;
-  const __nv_bfloat16* bias;   // [N] or null
-  const __nv_bfloat16* resid;  // [*, ldr] or null (EPI_RESID)
-  const float* resid32;        // EPI_RESID_F32
-  long long ldr;
-  const int* row_map;  // optional: output (and residual) row of A-row r is row_map[r]
-  int num_m, num_n, num_tiles;
-  int group_m;  // rasterisation: group_m M-tiles share one sweep over the N tiles (their A panels stay in L2)
-  int group_n;  // N super-tiles: all M groups sweep group_n N-tiles before the next group_n (that W sub-panel stays in L2)
-  int hints;    // bit 0: W loads L2 evict_last, bit 1: A loads evict_first, bit 2: streaming (evict-first) output stores
-  // --- implicit-GEMM convolution (CONV kernels only): A is an NHWC activation tensor [B, Hi, Wi, Cin] read through a
-  // 4-D TMA map; an M tile is a th x tw patch of output pixels (th*tw = 128) of one image; K runs over
-  // (tap, 64-channel chunk); output / residual rows are NHWC pixel indices.
-  int Ho, Wo;            // output spatial size
-  int tw, th;            // tile width / height in output pixels
-  int tiles_w, tiles_h;  // tiles per image
-  int ksize, pad;        // 1 or 3; left/top zero padding in input pixels
-  int stride;            // 1 or 2 (the TMA map carries the element stride)
-  int cin_chunks;        // Cin / 64
-  float* C32;            // optional fp32 output (EPI_F32)
-  QkvEpi qkv;            // EPI_QKV only
-};
 
 template <int BN>
 struct GemmCfg {
@@ -86,38 +33,6 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// Two-level raster. Outer: N super-tiles of group_n N-tiles (the W sub-panel of a super-tile, group_n * BN * K * 2 bytes, is
-// what should stay L2-resident while every M group sweeps it). Inner: groups of group_m M-tiles, M fastest, so the ~148
-// CTAs running at any moment cover group_m x (148 / group_m) tiles and share their A / W tiles through the L2.
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int group_n, int& m_blk,
-                                            int& n_blk) {
-  const int super_size = group_n * num_m;
-  const int s = tile / super_size;
-  const int n0 = s * group_n;
-  const int nn = min(group_n, num_n - n0);
-  const int rem = tile - s * super_size;
-  const int group_size = group_m * nn;
-  const int g = rem / group_size;
-  const int first_m = g * group_m;
-  const int gm = min(num_m - first_m, group_m);
-  const int local = rem - g * group_size;
-  m_blk = first_m + local % gm;
-  n_blk = n0 + local / gm;
-}
-
-__device__ __forceinline__ void store16(void* dst, const uint4& v, bool streaming) {
-  if (streaming) __stcs(reinterpret_cast<uint4*>(dst), v);   // st.global.cs: evict-first, the output is not re-read by this kernel
-  else *reinterpret_cast<uint4*>(dst) = v;
-}
-
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // torch "gelu_pytorch_tanh": 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -538,6 +453,14 @@ extern "C" int bagel_gemm_bf16(const void* A, long long lda, const void* W, long
   static const bool skinny_on = [] { const char* e = getenv("BAGEL_GEMM_SKINNY"); return !(e && atoi(e) == 0); }();
   if (skinny_on && gemm_skinny_supported(M, N, K, epilogue))
     return gemm_skinny(A, lda, W, ldw, C, ldc, M, N, K, bias, resid, ldr, row_map, epilogue, s);
+
+  // the large projections: 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2), gemm2.cu
+  if (gemm2_supported(M, N, K, epilogue)) {
+    CUtensorMap tmA2, tmB2;
+    if (int rc = make_tmap_2d_bf16(&tmA2, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return rc;
+    if (int rc = make_tmap_2d_bf16(&tmB2, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, 128)) return rc;
+    return gemm2_launch(tmA2, tmB2, p, epilogue, s);
+  }
 
   int bn;
   if (epilogue == EPI_SWIGLU) {

@@ -87,7 +87,9 @@ int bagel_gemm_qkv_norm_rope(const void* A, long long lda, const void* W, long l
  *   exactly what the reference passes); max_seqlen_k (host int, <= 0 if unknown) only tunes the key split of the
  *   single-query path: when max_seqlen_q == 1 (text decode, D = 128) a split-KV kernel streams the cache instead.
  *   seqused_k (optional int32[batch], device): number of keys in use per sample when the K/V rows of sample b start at
- *   cu_seqlens_k[b] but the buffer has spare capacity (append-in-place decode; same meaning as flash-attn's seqused_k). */
+ *   cu_seqlens_k[b] but the buffer has spare capacity (append-in-place decode; same meaning as flash-attn's seqused_k).
+ *   The spare rows must hold FINITE values (e.g. a zero-initialised slab): whole 128-key blocks are fetched by TMA and the
+ *   masked probabilities (exactly 0) are multiplied with them. */
 int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,
                           const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
                           int num_heads_k, int head_dim, int max_seqlen_q, int max_seqlen_k, int causal,

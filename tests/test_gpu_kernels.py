@@ -69,6 +69,46 @@ def test_gemm_swiglu_gelu_silu():
     _assert_bf16_close(ops.gemm(a, gw, epilogue=ops.EPI_SILU), torch.nn.functional.silu(y), ulps=4.0)
 
 
+PAIR_CASES = [  # M >= 512 and N % 256 == 0 route to the CTA-pair kernel (gemm2.cu, tcgen05 cta_group::2, 256x256 tiles)
+    (640, 768, 320),      # 5 M-tiles: the last pair has no peer rows (TMA zero-fill, stores masked)
+    (657, 512, 200),      # ragged M and a K tail (200 = 3 x 64 + 8)
+    (1153, 256, 64),      # one K block, one N tile
+    (2048, 4608, 3584),   # qkv-sized, 8 M-tile pairs x 18 N tiles: several tiles per cluster, both accumulator stages
+    (65568, 512, 128),    # the benchmark's M: 257 pairs, persistent loop with 7 tiles per cluster
+]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_CASES)
+def test_gemm_pair_bias_resid_swiglu_rowmap(M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, generator=g).to(torch.bfloat16)
+    mm = _mm(a, w)
+    _assert_bf16_close(ops.gemm(a, w, bias=b), mm + b.float())
+    _assert_bf16_close(ops.gemm(a, w), mm)
+    res = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)
+    out = ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID)
+    _assert_bf16_close(out, res.float() + mm.to(torch.bfloat16).float(), scale_ref=res.float().abs() + mm.abs())
+    assert torch.equal(out, ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID))          # deterministic
+    # SwiGLU: W = interleaved (gate | up) blocks of 128 rows -> the leader CTA stages the gate rows, its peer the up rows
+    gw, uw = w[: N // 2], w[N // 2:]
+    sw = ops.gemm(a, ops.interleave_gate_up(gw, uw), epilogue=ops.EPI_SWIGLU)
+    ref = (torch.nn.functional.silu(_mm(a, gw).to(torch.bfloat16)) * _mm(a, uw).to(torch.bfloat16)).float()
+    _assert_bf16_close(sw, ref, ulps=4.0)
+    # row_map scatter + residual gather through the map; rows outside the map untouched
+    if M <= 4096:
+        big = torch.full((M + 300, N), 7.0, device=DEV, dtype=torch.bfloat16)
+        rm = torch.randperm(M + 300, device=DEV, generator=g)[:M].to(torch.int32)
+        rbig = torch.randn(M + 300, N, device=DEV, generator=g).to(torch.bfloat16)
+        ops.gemm(a, w, resid=rbig, row_map=rm, epilogue=ops.EPI_RESID, out=big)
+        want = rbig[rm.long()].float() + mm.to(torch.bfloat16).float()
+        _assert_bf16_close(big[rm.long()], want, scale_ref=rbig[rm.long()].float().abs() + mm.abs())
+        untouched = torch.ones(M + 300, dtype=torch.bool, device=DEV)
+        untouched[rm.long()] = False
+        assert bool((big[untouched] == 7.0).all())
+
+
 SKINNY_CASES = [  # (M, N, K): decode projections of the 7B model + ragged / tiny shapes (swapped-operand split-K kernel)
     (1, 3584, 3584), (7, 4608, 3584), (16, 3584, 3584), (32, 3584, 18944), (33, 4608, 3584), (64, 3584, 3584),
     (32, 152064, 512), (5, 264, 72), (32, 1024, 320), (24, 2048, 64),

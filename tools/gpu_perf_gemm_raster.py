@@ -22,9 +22,11 @@ for (M, N, K, epi) in [(65568, 37888, 3584, 2), (65568, 3584, 18944, 1)]:
     res.append(f"N={N} K={K}: {t:.3f} ms {2.0*M*N*K/t/1e9:.0f} TF/s")
 print("   " + " | ".join(res), flush=True)
 '''
-cfgs = [(0, 0, 0), (0, 4, 0), (37, 0, 0), (37, 1, 0), (37, 5, 0), (37, 7, 0), (19, 1, 0), (19, 5, 0), (74, 5, 0),
-        (37, 5, 8), (37, 5, 32), (19, 5, 8)]
-for gn, h, gm in cfgs:
-    env = dict(os.environ, BAGEL_GEMM_GROUP_N=str(gn), BAGEL_GEMM_HINTS=str(h), BAGEL_GEMM_GROUP_M=str(gm))
-    print(f"group_n={gn} hints={h} group_m={gm or 'auto'}", flush=True)
+# (pair kernel on/off, group_n, hints, group_m in M-tiles)
+cfgs = [(0, 0, 0, 0), (1, 0, 0, 0), (0, 0, 4, 0), (1, 0, 4, 0), (1, 37, 5, 0), (1, 74, 5, 0), (1, 0, 0, 8), (1, 0, 0, 32),
+        (1, 37, 5, 32), (0, 0, 0, 0), (1, 0, 0, 0)]
+for pair, gn, h, gm in cfgs:
+    env = dict(os.environ, BAGEL_GEMM_PAIR=str(pair), BAGEL_GEMM_GROUP_N=str(gn), BAGEL_GEMM_HINTS=str(h),
+               BAGEL_GEMM_GROUP_M=str(gm))
+    print(f"pair={pair} group_n={gn} hints={h} group_m={gm or 'auto'}", flush=True)
     subprocess.run([sys.executable, "-c", code], env=env)
