@@ -694,6 +694,129 @@ class Bagel:
         return history[:steps].clone()
 
     # ------------------------------------------------------------------------------------------
+    # training-mode forward (losses only, no backward): reference Bagel.forward, bagel.py:101-229
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, sequence_length: int, packed_text_ids, packed_text_indexes, sample_lens: List[int],
+                packed_position_ids, nested_attention_masks=None, split_lens: List[int] = None,
+                attn_modes: List[str] = None, ce_loss_indexes=None, packed_label_ids=None, packed_vit_tokens=None,
+                packed_vit_token_indexes=None, packed_vit_position_ids=None, vit_token_seqlens=None, padded_latent=None,
+                patchified_vae_latent_shapes=None, packed_latent_position_ids=None, packed_vae_token_indexes=None,
+                packed_timesteps=None, mse_loss_indexes=None, noise: Optional[torch.Tensor] = None):
+        """The reference's training forward on a packed batch -> dict(mse=..., ce=...) (forward only: the B200 build has no
+        autograd; useful for evaluation losses / distillation targets with the inference kernels).
+
+        Attention structure (data/data_utils.py:13-40, 72-103): every sample is a list of splits that are 'causal' (text),
+        'full' (an image everyone after it may look at) or 'noise' (a noised image only it itself sees); a split attends to
+        all earlier non-noise splits of its sample plus itself. That is exactly a chain of prefill calls on a growing KV
+        cache — so instead of a block-sparse mask over the whole packed sequence, each split runs through the varlen
+        attention kernel against [cache || itself] (causal flag for text) and is appended to the cache unless it is
+        noise. Experts as in training: text + ViT tokens -> und weights, VAE tokens -> gen weights, with the training
+        modules' all-bf16 q/k-norm + RoPE flow (`train_numerics`). `split_lens` / `attn_modes` (the reference's
+        flex-attention inputs) are required; `nested_attention_masks` carries no extra information and is ignored.
+        `noise` overrides the torch.randn_like draw of :184."""
+        if split_lens is None or attn_modes is None:
+            raise NotImplementedError("Bagel.forward needs split_lens and attn_modes (dense nested_attention_masks alone "
+                                      "cannot be mapped onto the varlen attention kernel)")
+        if self.dtype_mode != "A":
+            raise NotImplementedError("Bagel.forward is implemented for dtype_mode='A'")
+        dev = self.device
+        lm = self.language_model.model
+        L = int(sequence_length)
+        H = self.hidden_size
+        i32 = lambda t: torch.as_tensor(t).to(dev, torch.int32).contiguous()
+        seq = torch.zeros((L, H), dtype=BF16, device=dev)
+        text_idx = torch.as_tensor(packed_text_indexes).to("cpu", torch.int64)
+        ops.copy_rows(lm.embed_tokens(torch.as_tensor(packed_text_ids)), seq, dst_rows=i32(text_idx))
+        kind = torch.zeros(L, dtype=torch.int8)          # 0 text (und), 1 ViT (und), 2 VAE (gen)
+        if self.config.visual_und and packed_vit_tokens is not None:
+            vl = torch.as_tensor(vit_token_seqlens).to("cpu", torch.int64)
+            cu = torch.cat([torch.zeros(1, dtype=torch.int64), vl.cumsum(0)]).to(torch.int32)
+            feats = self.connector(self.vit_model(packed_pixel_values=packed_vit_tokens,
+                                                  packed_flattened_position_ids=packed_vit_position_ids, cu_seqlens=cu,
+                                                  max_seqlen=int(vl.max())))
+            ops.latent_embed_add(feats, None, self.vit_pos_embed.pos_embed,
+                                 torch.as_tensor(packed_vit_position_ids).to(dev, torch.int64).contiguous(), seq,
+                                 i32(packed_vit_token_indexes))
+            kind[torch.as_tensor(packed_vit_token_indexes).to("cpu", torch.int64)] = 1
+        mse = None
+        if self.config.visual_gen and padded_latent is not None:
+            p, zc = self.latent_patch_size, self.latent_channel
+            rows = []
+            for lat, (h, w) in zip(torch.as_tensor(padded_latent), patchified_vae_latent_shapes):
+                lat = lat[:, : h * p, : w * p].reshape(zc, h, p, w, p)
+                rows.append(lat.permute(1, 3, 2, 4, 0).reshape(h * w, p * p * zc))
+            clean = torch.cat(rows, dim=0).to(dev, torch.float32)
+            if noise is None:
+                noise = torch.randn_like(clean)
+            noise = noise.to(dev, torch.float32)
+            t = torch.sigmoid(torch.as_tensor(packed_timesteps).to(dev, torch.float32))
+            t = self.timestep_shift * t / (1 + (self.timestep_shift - 1) * t)
+            x_t = ((1 - t[:, None]) * clean + t[:, None] * noise).contiguous()      # flow-matching interpolation (:185-187)
+            proj = ops.gemm(ops.cast_f32_to_bf16(x_t), self.vae2llm.weight, bias=self.vae2llm.bias)
+            t_emb = self.time_embedder(t)                                            # per token [M, H]
+            vae_idx = torch.as_tensor(packed_vae_token_indexes).to("cpu", torch.int64)
+            vae_rows = i32(vae_idx)
+            vae_pos = torch.as_tensor(packed_latent_position_ids).to(dev, torch.int64).contiguous()
+            off = 0
+            for (h, w) in patchified_vae_latent_shapes:     # all tokens of an image share its timestep embedding row
+                n = h * w
+                ops.latent_embed_add(proj[off:off + n], t_emb[off], self.latent_pos_embed.pos_embed, vae_pos[off:off + n], seq,
+                                     vae_rows[off:off + n])
+                off += n
+            kind[vae_idx] = 2
+        # ---- the LM: one chained prefill per split ----
+        hidden = torch.empty((L, H), dtype=BF16, device=dev)
+        pos_all = torch.as_tensor(packed_position_ids).to("cpu", torch.int64)
+        nl = lm.config.num_hidden_layers
+        s_iter = iter(zip(split_lens, attn_modes))
+        start = 0
+        for slen in sample_lens:
+            cache, kv_len, done = NaiveCache(nl), 0, 0
+            while done < slen:
+                n, amode = next(s_iter)
+                if amode not in ("causal", "full", "noise"):
+                    raise ValueError(f"unknown attn mode {amode!r}")
+                r0 = start + done
+                k = kind[r0:r0 + n]
+                vae_rel = torch.nonzero(k == 2).reshape(-1)
+                extra = {}
+                if self.use_moe and vae_rel.numel():
+                    extra = dict(mode="gen", packed_vae_token_indexes=vae_rel, packed_text_indexes=torch.nonzero(k != 2).reshape(-1))
+                out = lm.forward_inference(
+                    packed_query_sequence=seq[r0:r0 + n], query_lens=torch.tensor([n], dtype=torch.int32),
+                    packed_query_position_ids=pos_all[r0:r0 + n], packed_query_indexes=torch.arange(kv_len, kv_len + n),
+                    past_key_values=cache, key_values_lens=torch.tensor([kv_len], dtype=torch.int32),
+                    packed_key_value_indexes=torch.arange(kv_len), update_past_key_values=(amode != "noise"),
+                    is_causal=(amode == "causal"), train_numerics=True, **extra)
+                hidden[r0:r0 + n] = out.packed_query_sequence
+                if amode != "noise":
+                    kv_len += n
+                done += n
+            if done != slen:
+                raise ValueError("split_lens do not add up to sample_lens")
+            start += slen
+        self._last_hidden_state = hidden
+        # ---- heads / losses (:214-227) ----
+        if self.config.visual_gen and padded_latent is not None:
+            mrows = torch.nonzero(torch.as_tensor(mse_loss_indexes).to("cpu")).reshape(-1)
+            hm = torch.empty((mrows.numel(), H), dtype=BF16, device=dev)
+            ops.copy_rows(hidden, hm, src_rows=i32(mrows))
+            preds = ops.gemm(hm, self.llm2vae.weight, bias=self.llm2vae.bias)
+            target = noise - clean                           # v_t = dx_t/dt = x_1 - x_0
+            mse = (preds - target[t > 0]) ** 2
+        ce = None
+        if ce_loss_indexes is not None:
+            crow = torch.nonzero(torch.as_tensor(ce_loss_indexes).to("cpu")).reshape(-1)
+            hc = torch.empty((crow.numel(), H), dtype=BF16, device=dev)
+            ops.copy_rows(hidden, hc, src_rows=i32(crow))
+            logits = self.language_model.lm_head(hc)
+            ce = torch.nn.functional.cross_entropy(logits.float(), torch.as_tensor(packed_label_ids).to(dev), reduction="none")
+        return dict(mse=mse, ce=ce)
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------------------------------
     # evaluation entry point: images + prompt -> text (reference bagel.py:1004-1075)
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

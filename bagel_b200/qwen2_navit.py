@@ -97,7 +97,7 @@ class ForwardPlan:
 
     def __init__(self, lm: "Qwen2Model", query_lens, position_ids, packed_query_indexes, key_values_lens,
                  packed_key_value_indexes, is_causal: bool, mode: str, packed_vae_token_indexes=None,
-                 packed_text_indexes=None):
+                 packed_text_indexes=None, train_numerics: bool = False):
         dev = lm.device
         cfg = lm.config
         ql = torch.as_tensor(query_lens).to("cpu", torch.int64).reshape(-1)
@@ -120,6 +120,12 @@ class ForwardPlan:
         # q/k-norm + RoPE arithmetic in fp32 only in PackedAttentionMoT's gen branch (qwen2_navit.py:542-548); the dense
         # PackedAttention every other layer class uses is the bf16 flow whatever the mode (:325-336)
         self.fp32_flow = int((mode == "gen") and lm.layer_kind == "mot") + (2 if lm.dtype_mode == "B" else 0)
+        if train_numerics:
+            # the training-mode modules (PackedAttentionMoT.forward_train, qwen2_navit.py:406-449) have no fp32 upcast
+            # around q/k-norm and RoPE: gen tokens take the same all-bf16 flow as und tokens, only the weights differ
+            if lm.dtype_mode != "A":
+                raise NotImplementedError("training-forward numerics are implemented for dtype_mode='A'")
+            self.fp32_flow = 0
         self.q_rows = torch.as_tensor(packed_query_indexes).to(dev, torch.int32).contiguous()
         if self.n_ctx:
             self.ctx_rows = torch.as_tensor(packed_key_value_indexes).to(dev, torch.int32).contiguous()
@@ -314,7 +320,8 @@ class Qwen2Model:
     def forward_inference(self, packed_query_sequence, query_lens, packed_query_position_ids, packed_query_indexes,
                           past_key_values: Optional[NaiveCache] = None, key_values_lens=None,
                           packed_key_value_indexes=None, update_past_key_values=True, is_causal=True, mode="und",
-                          packed_vae_token_indexes=None, packed_text_indexes=None) -> BaseNavitOutputWithPast:
+                          packed_vae_token_indexes=None, packed_text_indexes=None,
+                          train_numerics: bool = False) -> BaseNavitOutputWithPast:
         if self.enable_taylorseer:
             raise NotImplementedError("the TaylorSeer step cache lives in the planned sampler: call "
                                       "Bagel.generate_image(enable_taylorseer=True) (bagel_b200/bagel.py FlowRunner)")
@@ -323,7 +330,7 @@ class Qwen2Model:
         has_ctx = past_key_values is not None and past_key_values.key_cache[0] is not None
         plan = ForwardPlan(self, query_lens, packed_query_position_ids, packed_query_indexes,
                            key_values_lens if has_ctx else None, packed_key_value_indexes if has_ctx else None,
-                           is_causal, mode, packed_vae_token_indexes, packed_text_indexes)
+                           is_causal, mode, packed_vae_token_indexes, packed_text_indexes, train_numerics)
         x = packed_query_sequence.to(self.device, self.stream_dtype)
         kbuf, vbuf = self.alloc_kv(plan)
         self.place_context(plan, past_key_values, kbuf, vbuf)

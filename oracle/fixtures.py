@@ -230,3 +230,87 @@ def inferencer_image(seed: int = 3, h: int = 40, w: int = 56):
     yy, xx = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
     img = np.stack([xx, yy, 0.5 + 0.5 * np.sin(6 * xx * yy)], -1) * 200 + rs.randint(0, 55, (h, w, 3))
     return Image.fromarray(img.clip(0, 255).astype(np.uint8))
+
+
+def train_batch():
+    """A hand-built packed TRAINING batch (the format of Bagel.forward, bagel.py:101-150) of two samples:
+      sample 0: text (causal) | ViT image (full) | noised VAE image (noise) | text (causal)
+      sample 1: clean VAE image (full, timestep -inf => t = 0) | text (causal) | noised VAE image (noise)
+    Deterministic; shared by the golden generator and the GPU test (tests/test_gpu_train_forward.py)."""
+    g = torch.Generator().manual_seed(31)
+    ds, max_lat, max_vit = 16, 8, 8
+    from . import bagel_flow as obf
+    vit_img = vit_images()[1]                      # 28 x 28 -> 2 x 2 patches
+    from . import siglip as osl
+    vit_tok = osl.patchify(vit_img, 14)
+    lat_shapes = [(4, 4), (2, 4), (2, 2)]                   # latent patch grids (h, w) of the three VAE images
+    padded_latent = torch.zeros(3, 16, 8, 8)
+    for i, (h, w) in enumerate(lat_shapes):
+        padded_latent[i, :, : 2 * h, : 2 * w] = torch.randn(16, 2 * h, 2 * w, generator=g)
+    SOI, EOI = 1002, 1003
+    text_ids, text_idx, vit_idx, vae_idx, pos, ce_idx, labels = [], [], [], [], [], [], []
+    lat_pos, timesteps, mse_idx = [], [], []
+    sample_lens, split_lens, attn_modes = [], [], []
+    cur = 0
+
+    def add_text(ids, rope, with_loss):
+        nonlocal cur
+        for k, t in enumerate(ids):
+            text_ids.append(t); text_idx.append(cur); pos.append(rope + k)
+            if with_loss and k < len(ids) - 1:
+                ce_idx.append(cur); labels.append(ids[k + 1])
+            cur += 1
+        return rope + len(ids)
+
+    def add_vit(rope):
+        nonlocal cur
+        text_ids.append(SOI); text_idx.append(cur); cur += 1
+        vit_idx.extend(range(cur, cur + vit_tok.shape[0])); cur += vit_tok.shape[0]
+        text_ids.append(EOI); text_idx.append(cur); cur += 1
+        pos.extend([rope] * (vit_tok.shape[0] + 2))
+        return rope + 1, vit_tok.shape[0] + 2
+
+    def add_vae(i, rope, t):
+        nonlocal cur
+        h, w = lat_shapes[i]
+        n = h * w
+        text_ids.append(SOI); text_idx.append(cur); cur += 1
+        vae_idx.extend(range(cur, cur + n))
+        if t != float("-inf"):
+            mse_idx.extend(range(cur, cur + n))
+        cur += n
+        text_ids.append(EOI); text_idx.append(cur); cur += 1
+        pos.extend([rope] * (n + 2))
+        lat_pos.append(obf.flattened_position_ids(h * ds, w * ds, ds, max_lat))
+        timesteps.extend([t] * n)
+        return rope + 1, n + 2
+
+    # sample 0
+    start = cur
+    r = add_text([1000, 5, 17, 900, 33, 1001], 0, True); s0 = [6]; m0 = ["causal"]
+    r, n = add_vit(r); s0.append(n); m0.append("full")
+    r, n = add_vae(0, r, 0.3); s0.append(n); m0.append("noise")
+    r = add_text([1000, 8, 100, 4, 1001], r, True); s0.append(5); m0.append("causal")
+    sample_lens.append(cur - start); split_lens += s0; attn_modes += m0
+    # sample 1
+    start = cur
+    r, n = add_vae(1, 0, float("-inf")); s1 = [n]; m1 = ["full"]
+    r = add_text([1000, 77, 650, 12, 9, 1001], r, False); s1.append(6); m1.append("causal")
+    r, n = add_vae(2, r, -0.8); s1.append(n); m1.append("noise")
+    sample_lens.append(cur - start); split_lens += s1; attn_modes += m1
+    L = cur
+    ce_mask = torch.zeros(L, dtype=torch.bool); ce_mask[ce_idx] = True
+    mse_mask = torch.zeros(L, dtype=torch.bool); mse_mask[mse_idx] = True
+    return dict(
+        sequence_length=L, packed_text_ids=torch.tensor(text_ids), packed_text_indexes=torch.tensor(text_idx),
+        sample_lens=sample_lens, packed_position_ids=torch.tensor(pos), split_lens=split_lens, attn_modes=attn_modes,
+        nested_split_lens=[s0, s1], nested_attn_modes=[m0, m1],
+        ce_loss_indexes=ce_mask, packed_label_ids=torch.tensor(labels), packed_vit_tokens=vit_tok,
+        packed_vit_token_indexes=torch.tensor(vit_idx),
+        packed_vit_position_ids=obf.flattened_position_ids(28, 28, 14, max_vit),
+        vit_token_seqlens=torch.tensor([vit_tok.shape[0]], dtype=torch.int), padded_latent=padded_latent,
+        patchified_vae_latent_shapes=lat_shapes, packed_latent_position_ids=torch.cat(lat_pos),
+        packed_vae_token_indexes=torch.tensor(vae_idx), packed_timesteps=torch.tensor(timesteps),
+        mse_loss_indexes=mse_mask)
+
+

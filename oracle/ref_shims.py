@@ -8,6 +8,9 @@ Shims (the reference itself is untouched):
   2. Qwen2Config no longer defaults pad_token_id (read at modeling/bagel/qwen2_navit.py:946);
   3. flash_attn_varlen_func has no CPU kernel -> per-sequence fp32 SDPA on the bf16 inputs, bottom-right
      aligned causal mask, GQA by head repetition (the documented semantics of flash-attn >= 2.1).
+  4. (training forward only) `sdpa_kernel(backends=[EFFICIENT_ATTENTION])` around the masked SDPA call of
+     PackedAttentionMoT.forward_train (qwen2_navit.py:462) selects a CUDA kernel and leaves no viable backend on the
+     CPU -> replaced by a no-op context manager, i.e. torch's default CPU SDPA on the same operands.
 """
 from __future__ import annotations
 
@@ -92,6 +95,8 @@ def load_reference():
 
     qn.flash_attn_varlen_func = cpu_varlen_attention
     sn.flash_attn_varlen_func = cpu_varlen_attention
+    import contextlib
+    qn.sdpa_kernel = lambda *a, **k: contextlib.nullcontext()
     ns.qwen2_navit, ns.siglip_navit, ns.bagel, ns.modeling_utils = qn, sn, bg, mu
     ns.autoencoder, ns.modeling_qwen2, ns.data_utils = ae, mq, du
     try:

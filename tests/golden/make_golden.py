@@ -611,6 +611,51 @@ def golden_mode_b(ns):
     save_file(out, os.path.join(OUT, "mode_b_tiny.safetensors"))
 
 
+def golden_train_forward(ns):
+    """Bagel.forward in training mode (bagel.py:101-229; forward_train paths qwen2_navit.py:406-497, 713-755, 970-1016)
+    with dense per-sample masks (data/data_utils.py:72-103): losses + last hidden state of the reference; also asserts
+    that oracle/train_forward.py reproduces it bit for bit."""
+    from oracle import siglip as osl, train_forward as otf
+    model, sd_full, cfg, tv = _ref_bagel_with_vit(ns, rope=False)
+    model.config.timestep_shift = 1.0
+    b = fixtures.train_batch()
+    masks = [ns.data_utils.prepare_attention_mask_per_sample(s, m) for s, m in zip(b["nested_split_lens"], b["nested_attn_modes"])]
+    omasks = [otf.prepare_attention_mask_per_sample(s, m) for s, m in zip(b["nested_split_lens"], b["nested_attn_modes"])]
+    for a, c in zip(masks, omasks):
+        assert torch.equal(a, c)
+    hidden = {}
+    hook = model.language_model.model.register_forward_hook(lambda m, i, o: hidden.__setitem__("h", o.detach().clone()))
+    model.train()
+    kw = {k: v for k, v in b.items() if k not in ("split_lens", "attn_modes", "nested_split_lens", "nested_attn_modes")}
+    torch.manual_seed(7)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        out = model(nested_attention_masks=masks, **kw)
+    hook.remove()
+    model.eval()
+    # the same noise draw the reference made (first RNG use inside forward: torch.randn_like(packed_latent_clean), :184)
+    n_lat = sum(h * w for h, w in b["patchified_vae_latent_shapes"])
+    torch.manual_seed(7)
+    noise = torch.randn(n_lat, 64)
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"])
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    with torch.no_grad():
+        o = otf.bagel_forward_train(
+            sd_full, fc, b["sequence_length"], b["packed_text_ids"], b["packed_text_indexes"], b["sample_lens"],
+            b["packed_position_ids"], omasks, noise, timestep_shift=1.0, ce_loss_indexes=b["ce_loss_indexes"],
+            packed_label_ids=b["packed_label_ids"],
+            vit=(vc, b["packed_vit_tokens"], b["packed_vit_token_indexes"], b["packed_vit_position_ids"], b["vit_token_seqlens"]),
+            padded_latent=b["padded_latent"], patchified_vae_latent_shapes=b["patchified_vae_latent_shapes"],
+            packed_latent_position_ids=b["packed_latent_position_ids"], packed_vae_token_indexes=b["packed_vae_token_indexes"],
+            packed_timesteps=b["packed_timesteps"], mse_loss_indexes=b["mse_loss_indexes"])
+    assert torch.equal(o["last_hidden_state"], hidden["h"]), "oracle forward_train hidden != reference"
+    assert torch.equal(o["mse"], out["mse"]) and torch.equal(o["ce"], out["ce"]), "oracle losses != reference"
+    print("train forward: oracle == reference (bit-exact); mse mean", float(out["mse"].mean()), "ce mean", float(out["ce"].mean()))
+    save_file({"train.mse": out["mse"].contiguous(), "train.ce": out["ce"].contiguous(),
+               "train.last_hidden_state": hidden["h"].contiguous(), "train.noise": noise},
+              os.path.join(OUT, "train_forward_tiny.safetensors"))
+
+
 def _ref_bagel_with_vit(ns, rope):
     cfg = fixtures.TINY_LM
     dtype = torch.bfloat16
@@ -691,6 +736,7 @@ def main():
         golden_vit_rope(ns)
         golden_chat(ns)
         golden_mode_b(ns)
+        golden_train_forward(ns)
         return
     golden_lm_config1(ns)
     golden_flow(ns)
@@ -701,6 +747,7 @@ def main():
     golden_vit_rope(ns)
     golden_chat(ns)
     golden_mode_b(ns)
+    golden_train_forward(ns)
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".safetensors")}
     print("wrote", sizes)
 

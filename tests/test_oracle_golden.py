@@ -197,3 +197,82 @@ def test_vae_context_prefill_bit_exact(golden_dir):
     last = cfg.num_hidden_layers - 1
     assert torch.equal(c.key_cache[last], g["vae_ctx.k_cache_last"])
     assert torch.equal(c.value_cache[last], g["vae_ctx.v_cache_last"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2 fixtures: decoder-layer variants, SigLIP 2-D RoPE, training forward (all generated by make_golden.py --new-only)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,cfg", [("dense", fixtures.TINY_DENSE_LM), ("moe", fixtures.TINY_MOE_LM)])
+def test_dense_and_moe_layers_bit_exact(golden_dir, tag, cfg):
+    g = load_file(os.path.join(golden_dir, "lm_variants.safetensors"))
+    sd = fixtures.lm_state_dict(cfg, seed=0)
+    assert ("model.layers.0.mlp_moe_gen.up_proj.weight" in sd) == (tag == "moe")
+    assert "model.layers.0.self_attn.q_proj_moe_gen.weight" not in sd
+    inp = fixtures.config1_inputs(cfg)
+    with torch.no_grad():
+        cache = om.KVCache(cfg.num_hidden_layers)
+        h, cache = om.lm_forward_inference(sd, cfg, inp["x"], inp["query_lens"], inp["und_position_ids"], inp["query_indexes"],
+                                           cache, torch.tensor([0], dtype=torch.int32), torch.zeros(0, dtype=torch.long),
+                                           True, True, "und")
+    assert torch.equal(h, g[tag + ".und_hidden"])
+    assert torch.equal(cache.key_cache[cfg.num_hidden_layers - 1], g[tag + ".k_cache_last"])
+
+
+def test_vit_rope_bit_exact(golden_dir):
+    from oracle import siglip as osl
+    g = load_file(os.path.join(golden_dir, "vit_rope_tiny.safetensors"))
+    gin = load_file(os.path.join(golden_dir, "vit_tiny.safetensors"))
+    tv = fixtures.TINY_VIT
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"], rope=True, image_size=112)
+    with torch.no_grad():
+        f = osl.vit_forward(helpers.vit_flow_state_dict(fixtures.TINY_LM), vc, gin["vit_in.packed_vit_tokens"],
+                            gin["vit_in.packed_vit_position_ids"], gin["vit_in.vit_token_seqlens"])
+    assert torch.equal(f, g["vit_rope.features"])
+
+
+def test_training_forward_bit_exact(golden_dir):
+    """Bagel.forward in train() mode (oracle/train_forward.py) against the reference's losses and hidden states."""
+    from oracle import siglip as osl, train_forward as otf
+    g = load_file(os.path.join(golden_dir, "train_forward_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    tv = fixtures.TINY_VIT
+    b = fixtures.train_batch()
+    masks = [otf.prepare_attention_mask_per_sample(s, m) for s, m in zip(b["nested_split_lens"], b["nested_attn_modes"])]
+    # mask algebra (data/data_utils.py:72-103): sample 0 = text | ViT (full) | noised VAE (noise) | text
+    m0, (a, v, z, t2) = masks[0], b["nested_split_lens"][0]
+    assert torch.isinf(m0[0, 1]) and m0[1, 0] == 0                       # causal text
+    assert m0[a, a + v - 1] == 0 and m0[a + v - 1, a] == 0               # full image block, both directions
+    assert torch.isinf(m0[a + v + z, a + v]).item() and m0[a + v, a + v + z - 1] == 0   # later text cannot see the noise split
+    assert m0[a + v + z, a] == 0                                         # ...but sees the ViT image
+    vc = osl.VitConfig(hidden_size=tv["hidden"], intermediate_size=tv["inter"], num_hidden_layers=tv["layers"],
+                       num_attention_heads=tv["heads"])
+    with torch.no_grad():
+        o = otf.bagel_forward_train(
+            helpers.vit_flow_state_dict(cfg, max_latent_size=8), obf.FlowConfig(lm=cfg, max_latent_size=8), b["sequence_length"],
+            b["packed_text_ids"], b["packed_text_indexes"], b["sample_lens"], b["packed_position_ids"], masks, g["train.noise"],
+            timestep_shift=1.0, ce_loss_indexes=b["ce_loss_indexes"], packed_label_ids=b["packed_label_ids"],
+            vit=(vc, b["packed_vit_tokens"], b["packed_vit_token_indexes"], b["packed_vit_position_ids"], b["vit_token_seqlens"]),
+            padded_latent=b["padded_latent"], patchified_vae_latent_shapes=b["patchified_vae_latent_shapes"],
+            packed_latent_position_ids=b["packed_latent_position_ids"], packed_vae_token_indexes=b["packed_vae_token_indexes"],
+            packed_timesteps=b["packed_timesteps"], mse_loss_indexes=b["mse_loss_indexes"])
+    assert torch.equal(o["last_hidden_state"], g["train.last_hidden_state"])
+    assert torch.equal(o["mse"], g["train.mse"]) and torch.equal(o["ce"], g["train.ce"])
+
+
+def test_mode_b_flow_bit_exact(golden_dir):
+    """fp32 master weights under autocast (eval drivers): text prefill + 3-evaluation generate_image, d64."""
+    g = load_file(os.path.join(golden_dir, "mode_b_tiny.safetensors"))
+    cfg = fixtures.TINY_LM
+    sd = helpers.flow_state_dict(cfg, torch.float32)
+    fc = obf.FlowConfig(lm=cfg, max_latent_size=8)
+    tok = helpers.IntTokenizer()
+    with torch.no_grad():
+        gp, kv, rp = obf.prepare_prompts([0, 0], [0, 0], [tok.encode(p) for p in helpers.PROMPTS], 1000, 1001)
+        cache = obf.forward_cache_update_text(sd, fc, om.KVCache(cfg.num_hidden_layers), **gp)
+        assert torch.equal(cache.key_cache[cfg.num_hidden_layers - 1], g["d64.prefill.k_cache_last"])
+        torch.manual_seed(2)
+        gi = obf.prepare_vae_latent(fc, kv, rp, helpers.IMAGE_SIZES, 1002, 1003)
+        lat = obf.generate_image(sd, fc, gi, cache, num_timesteps=4, timestep_shift=3.0, cfg_renorm_type="global",
+                                 cfg_interval=[0.4, 1.0])
+    assert torch.equal(torch.cat(lat, 0), g["d64.gen.nocfg.latents"])
