@@ -51,6 +51,8 @@ SIGNATURES = {
     "bagel_taylor_eval_bf16": (_i, [_vp, _ll, _i, _i, _vp, _ll, _i, _i, _vp]),
     "bagel_rmsnorm_f32": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "bagel_latent_embed_add_f32": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _vp]),
+    "bagel_image_resize_bicubic_u8": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "bagel_image_normalize_u8": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _ll, _i, _vp]),
     "bagel_siglip_rope2d_bf16": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

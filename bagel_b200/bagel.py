@@ -262,10 +262,17 @@ class Bagel:
         rope = torch.tensor(list(curr_rope), dtype=torch.int64)
         tokens, pos = [], []
         for image in images:
-            t = transforms(image)
-            pos.append(self.get_flattened_position_ids(t.size(1), t.size(2), self.vit_patch_size,
+            if hasattr(transforms, "patches") and hasattr(image, "size") and not torch.is_tensor(image):
+                # device-side image path (transforms.DeviceImageTransform): resize + normalise + patchify on the GPU,
+                # bit-identical to the host path below
+                w_, h_ = transforms.resize_transform.target_size(*image.size)
+                tokens.append(transforms.patches(image, self.vit_patch_size))
+            else:
+                t = transforms(image)
+                h_, w_ = t.size(1), t.size(2)
+                tokens.append(patchify(t, self.vit_patch_size))
+            pos.append(self.get_flattened_position_ids(h_, w_, self.vit_patch_size,
                                                        max_num_patches_per_side=self.vit_max_num_patch_per_side))
-            tokens.append(patchify(t, self.vit_patch_size))
         ntok = torch.tensor([x.shape[0] for x in tokens], dtype=torch.int64)
         ql = ntok + 2
         q_start = torch.cumsum(ql, 0) - ql
@@ -335,7 +342,7 @@ class Bagel:
         B = len(images)
         C = tensors[0].shape[0]
         Hm, Wm = max(t.shape[1] for t in tensors), max(t.shape[2] for t in tensors)
-        padded = torch.zeros((B, C, Hm, Wm))
+        padded = torch.zeros((B, C, Hm, Wm), device=tensors[0].device)   # stays on the GPU with DeviceImageTransform
         for i, t in enumerate(tensors):
             padded[i, :, : t.shape[1], : t.shape[2]] = t
         generation_input = {

@@ -87,7 +87,8 @@ struct AttnItem {
   int q_beg, Lq, k_beg, Lk;
   int q0;            // first query row (within the sample)
   int shift;         // bottom-right aligned causal: key kv visible to query qi iff kv <= qi + shift
-  int nblk;          // key blocks to sweep
+  int nblk;          // key blocks to load (= the larger of the two tiles' counts)
+  int nblk_t[2];     // key blocks each tile sweeps: under a causal mask tile 0 stops one block before tile 1
   bool valid;        // q0 < Lq
   bool tile1_active;
 };
@@ -110,12 +111,17 @@ __device__ __forceinline__ AttnItem attn_decode_item(int item, const AttnParams&
   w.valid = w.q0 < w.Lq;
   w.tile1_active = (w.q0 + kBlockM) < w.Lq;
   w.shift = w.Lk - w.Lq;
-  int kv_end = w.Lk;
-  if (p.causal) {
-    const int q_hi = min(w.Lq, w.q0 + 2 * kBlockM) - 1;
-    kv_end = max(0, min(w.Lk, q_hi + w.shift + 1));
+  w.nblk_t[0] = w.nblk_t[1] = 0;
+  for (int t = 0; t < 2; ++t) {
+    if (!w.valid || (t == 1 && !w.tile1_active)) continue;
+    int kv_end = w.Lk;
+    if (p.causal) {   // last key any row of this tile may see
+      const int q_hi = min(w.Lq, w.q0 + (t + 1) * kBlockM) - 1;
+      kv_end = max(0, min(w.Lk, q_hi + w.shift + 1));
+    }
+    w.nblk_t[t] = (kv_end + kBlockN - 1) / kBlockN;
   }
-  w.nblk = w.valid ? (kv_end + kBlockN - 1) / kBlockN : 0;
+  w.nblk = max(w.nblk_t[0], w.nblk_t[1]);   // causal: tile 1 sees at least as many keys as tile 0
   return w;
 }
 
@@ -271,10 +277,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         mbar_wait(q_full, q_phase);
         q_phase ^= 1;
-        // block 0 scores for both tiles
+        // block 0 scores for both tiles (a tile with no visible key at all — causal, Lq > Lk — sweeps nothing)
         mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
-        for (int t = 0; t < ntile; ++t) issue_qk(t, stage);
+        for (int t = 0; t < ntile; ++t)
+          if (w.nblk_t[t] > 0) issue_qk(t, stage);
         umma_commit(&kv_empty[stage]);  // K_0 slot free once both S(0) are done
         if (nblk == 1) umma_commit(q_empty);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -291,20 +298,23 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tc_fence_after();
           for (int t = 0; t < ntile; ++t) {
+            if (j >= w.nblk_t[t]) continue;      // causal: this block lies entirely above the tile's diagonal
+            const bool t_next = (j + 1) < w.nblk_t[t];
             mbar_wait(&p_bar[t], pcnt[t] & 1);  // P_t(j) in TMEM, O_t rescaled
             ++pcnt[t];
             if (j == 0) mbar_wait(&o_free[t], (icnt[t] & 1) ^ 1);   // the previous item's O_t has been read out
             tc_fence_after();
             issue_pv(t, vstage, j > 0);
-            if (!has_next) umma_commit(&o_bar[t]);
+            if (!t_next) umma_commit(&o_bar[t]);
             // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
-            if (has_next) issue_qk(t, kstage);
+            if (t_next) issue_qk(t, kstage);
           }
           umma_commit(&kv_empty[vstage]);
           if (has_next) umma_commit(&kv_empty[kstage]);
           if (has_next && j + 2 == nblk) umma_commit(q_empty);   // that was the item's last QK^T
         }
-        for (int t = 0; t < ntile; ++t) ++icnt[t];
+        for (int t = 0; t < ntile; ++t)
+          if (w.nblk_t[t] > 0) ++icnt[t];
       }
     }
   } else {
@@ -331,7 +341,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (item >= p.num_items) break;
       const AttnItem w = attn_decode_item(item, p);
       if (!w.valid || (t == 1 && !w.tile1_active)) continue;
-      const int nblk = w.nblk;
+      const int nblk = w.nblk_t[t];
       const int Lq = w.Lq, Lk = w.Lk, shift = w.shift;
       const int qi = w.q0 + t * kBlockM + row;  // query index within the sample
 

@@ -458,3 +458,43 @@ def copy_rows_f32(src: torch.Tensor, dst: torch.Tensor, src_rows=None, dst_rows=
     """Row gather/scatter of fp32 rows through the bf16 copy kernel (a pure byte copy: each fp32 row is 2H bf16 lanes)."""
     _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
     return copy_rows(src.view(torch.bfloat16), dst.view(torch.bfloat16), src_rows, dst_rows, M)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-side image preprocessing (uint8 HWC images)
+# ---------------------------------------------------------------------------------------------------------------------
+def image_resize_bicubic_u8(src: torch.Tensor, Ho: int, Wo: int, taps_h, taps_v) -> torch.Tensor:
+    """Pillow-exact 8-bit bicubic resize of a uint8 [Hi, Wi, 3] CUDA image. taps_* = (kk int32 [out, ksize], bounds int32
+    [out, 2], ksize) from bagel_b200.transforms.pil_bicubic_coeffs, or None for an axis whose size does not change."""
+    _req(src, torch.uint8, "src")
+    assert src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous()
+    Hi, Wi = int(src.shape[0]), int(src.shape[1])
+    assert (taps_h is not None) == (Wo != Wi) and (taps_v is not None) == (Ho != Hi)
+    dst = torch.empty((Ho, Wo, 3), dtype=torch.uint8, device=src.device)
+    tmp = torch.empty((Hi, Wo, 3), dtype=torch.uint8, device=src.device) if (taps_h is not None and taps_v is not None) else None
+    kh, bh, ksh = taps_h if taps_h is not None else (None, None, 0)
+    kv, bv, ksv = taps_v if taps_v is not None else (None, None, 0)
+    for t, n_out in ((kh, Wo), (kv, Ho)):
+        if t is not None:
+            _req(t, torch.int32, "taps"); assert t.is_contiguous() and t.shape[0] == n_out
+    rc = _cabi.lib().bagel_image_resize_bicubic_u8(_ptr(src), Hi, Wi, _ptr(dst), Ho, Wo, _ptr(tmp), _ptr(kh), _ptr(bh), int(ksh),
+                                                   _ptr(kv), _ptr(bv), int(ksv), _stream())
+    _cabi.check(rc, "bagel_image_resize_bicubic_u8")
+    return dst
+
+
+def image_normalize_u8(src: torch.Tensor, mean, std, patch: int = 0) -> torch.Tensor:
+    """uint8 [H, W, 3] -> fp32 ((u8/255) - mean) / std: planar [3, H, W] (patch = 0) or patch rows [(H/p)(W/p), p*p*3]."""
+    _req(src, torch.uint8, "src")
+    assert src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous()
+    H, W = int(src.shape[0]), int(src.shape[1])
+    if patch:
+        out = torch.empty(((H // patch) * (W // patch), patch * patch * 3), dtype=torch.float32, device=src.device)
+        ld = out.stride(0)
+    else:
+        out = torch.empty((3, H, W), dtype=torch.float32, device=src.device)
+        ld = 0
+    rc = _cabi.lib().bagel_image_normalize_u8(_ptr(src), H, W, float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]),
+                                              float(std[1]), float(std[2]), _ptr(out), ld, int(patch), _stream())
+    _cabi.check(rc, "bagel_image_normalize_u8")
+    return out

@@ -227,6 +227,22 @@ int bagel_latent_embed_add_f32(const void* proj, long long ldp, const void* t_em
                                const long long* pos_ids, float* seq, long long lds, const int* dst_rows, int M, int H,
                                void* stream);
 
+/* Device-side image preprocessing (the reference does this on the host: data/transforms.py:15-115 -> PIL, then
+ * data/data_utils.py:43-50 patchify). BIT-EXACT w.r.t. Pillow's 8-bit bicubic resampler (antialiased, a = -0.5) and torch's
+ * ToTensor + Normalize arithmetic.
+ *   bagel_image_resize_bicubic_u8: src uint8 [Hi, Wi, 3] -> dst uint8 [Ho, Wo, 3]; horizontal pass then vertical pass,
+ *     out = clip8((2^21 + sum_k in[xmin+k] * kk[k]) >> 22); kk_* int32 [out_size, ksize_*] fixed-point taps (2^22) and
+ *     bounds_* int32 [out_size, 2] = (xmin, n) per output index, both computed by the host exactly as Pillow's
+ *     precompute_coeffs / normalize_coeffs_8bpc (bagel_b200.transforms.pil_bicubic_coeffs); tmp uint8 [Hi, Wo, 3].
+ *   bagel_image_normalize_u8: value = ((u8 / 255) - mean[c]) / std[c] in fp32 (three roundings, as torch);
+ *     patch == 0: out fp32 planar [3, H, W];  patch > 0: out fp32 [(H/patch)*(W/patch), ld] patch rows in (row-in-patch,
+ *     col-in-patch, channel) order — the `packed_vit_tokens` layout. */
+int bagel_image_resize_bicubic_u8(const uint8_t* src, int Hi, int Wi, uint8_t* dst, int Ho, int Wo, uint8_t* tmp,
+                                  const int* kk_h, const int* bounds_h, int ksize_h, const int* kk_v, const int* bounds_v,
+                                  int ksize_v, void* stream);
+int bagel_image_normalize_u8(const uint8_t* src, int H, int W, float mean0, float mean1, float mean2, float std0, float std1,
+                             float std2, float* out, long long ld, int patch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
