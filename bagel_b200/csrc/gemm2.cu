@@ -259,9 +259,10 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     static const int env_g = [] { const char* e = getenv("BAGEL_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
     static const int env_n = [] { const char* e = getenv("BAGEL_GEMM_GROUP_N"); return e ? atoi(e) : -1; }();
     static const int env_h = [] { const char* e = getenv("BAGEL_GEMM_HINTS"); return e ? atoi(e) : -1; }();
-    // 74 clusters in flight cover group_m pairs x (74 / group_m) N tiles: 8 x 9 keeps the unique operand bytes per wave
-    // minimal (the same 16 M-tiles x 9 N-tiles footprint the 1-CTA kernel's raster uses)
-    p.group_m = env_g > 0 ? (env_g + 1) / 2 : (p.num_n >= 64 ? 8 : 16);
+    // 74 clusters in flight cover group_m pairs x (74 / group_m) N tiles. Measured INSIDE the power-capped denoising step on
+    // one box (profiles/r02_gemm_pair_ab.txt): groups of 16 pairs (32 M tiles: W is streamed from DRAM 16x instead of 32x
+    // per launch, the 29 MB A panel of a group stays L2-resident) 809-811 ms per step, 8 pairs 836 ms, 1-CTA kernel 816 ms.
+    p.group_m = env_g > 0 ? (env_g + 1) / 2 : 16;
     int gn = env_n >= 0 ? env_n : 0;
     if (gn <= 0 || gn > p.num_n) gn = p.num_n;
     p.group_n = gn;

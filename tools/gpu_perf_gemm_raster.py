@@ -23,8 +23,8 @@ for (M, N, K, epi) in [(65568, 37888, 3584, 2), (65568, 3584, 18944, 1)]:
 print("   " + " | ".join(res), flush=True)
 '''
 # (pair kernel on/off, group_n, hints, group_m in M-tiles)
-cfgs = [(0, 0, 0, 0), (1, 0, 0, 0), (0, 0, 4, 0), (1, 0, 4, 0), (1, 37, 5, 0), (1, 74, 5, 0), (1, 0, 0, 8), (1, 0, 0, 32),
-        (1, 37, 5, 32), (0, 0, 0, 0), (1, 0, 0, 0)]
+cfgs = [(0, 0, 0, 0), (1, 0, 0, 0), (1, 0, 0, 24), (1, 0, 0, 32), (1, 0, 0, 48), (1, 0, 0, 64), (1, 0, 4, 16), (1, 0, 4, 32),
+        (1, 0, 4, 48), (1, 37, 5, 32), (1, 0, 6, 32), (0, 0, 0, 0), (1, 0, 0, 32)]
 for pair, gn, h, gm in cfgs:
     env = dict(os.environ, BAGEL_GEMM_PAIR=str(pair), BAGEL_GEMM_GROUP_N=str(gn), BAGEL_GEMM_HINTS=str(h),
                BAGEL_GEMM_GROUP_M=str(gm))
