@@ -81,8 +81,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : kEvictNormal;
-      const uint64_t hint_w = (p.hints & 1) ? kEvictLast : kEvictNormal;
+      const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : ((p.hints & 8) ? kEvictLast : kEvictNormal);
+      const uint64_t hint_w = (p.hints & 1) ? kEvictLast : ((p.hints & 16) ? kEvictFirst : kEvictNormal);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(tile, p.num_m, p.num_n, p.group_m, p.group_n, m_blk, n_blk);
@@ -335,13 +335,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 x1 = silu_f(bf16_round(x1));
               }
               if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
-                float* d32 = p.C32 + out_row * p.ldc + n0 + 2 * j;
-                if (n0 + 2 * j < p.N) *reinterpret_cast<float2*>(d32) = make_float2(x0, x1);
+                v[2 * j] = __float_as_uint(x0);     // reuse the accumulator registers for the fp32 result
+                v[2 * j + 1] = __float_as_uint(x1);
               }
               o[j] = pack_bf16x2(x0, x1);
             }
             if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
-              // fp32 result already stored above
+              float* d32 = p.C32 + out_row * p.ldc + n0;   // 128 contiguous bytes of this thread's row: 16-byte stores
+              if (full) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  reinterpret_cast<uint4*>(d32)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < p.N) d32[j] = __uint_as_float(v[j]);
+              }
             } else if (full) {
               uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
 #pragma unroll

@@ -86,8 +86,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : kEvictNormal;
-      const uint64_t hint_w = (p.hints & 1) ? kEvictLast : kEvictNormal;
+      const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : ((p.hints & 8) ? kEvictLast : kEvictNormal);
+      const uint64_t hint_w = (p.hints & 1) ? kEvictLast : ((p.hints & 16) ? kEvictFirst : kEvictNormal);
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         int mp, n_blk;
         tile_coords(tile, p.num_m, p.num_n, p.group_m, p.group_n, mp, n_blk);

@@ -13,8 +13,12 @@ namespace bagel {
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics, pass 1: partial (sum, sum of squares) per (image, slab, group).
 // x: [B, HW, C] bf16 (NHWC), G groups of C/G consecutive channels. Deterministic: no atomics, the slabs are
-// reduced in a fixed order by pass 2.
+// reduced in a fixed order by pass 2. HBM-bound: the grid is sized so that every SM holds several CTAs and every
+// thread keeps four 16-byte loads in flight (round 1 launched 64 CTAs with one load per thread in flight per image:
+// 0.24 TB/s at 1024^2 x 128 channels, a third of the whole VAE decode — profiles/r02_vae_decode_launches.csv).
 // ---------------------------------------------------------------------------------------------
+constexpr int kGnMaxSlabs = 1024;
+
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, long long HW, int C, int G,
                   int slabs) {
@@ -26,22 +30,29 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part
   const uint4* base = reinterpret_cast<const uint4*>(x + ((long long)b * HW + pix0) * C);
   __shared__ float4 part[256];  // per-thread (s0, q0, s1, q1); reduced in a fixed order -> deterministic
   // a thread always visits the same vector slot of a pixel (blockDim % vec_per_pix == 0 is guaranteed by the host:
-  // vec_per_pix in {8,16,32,64}), so its channels -> groups mapping is fixed
+  // vec_per_pix in {16,32,64}), so its channels -> groups mapping is fixed
   const int slot = threadIdx.x % vec_per_pix;
   const int c0 = slot * 8;
   float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
-  const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;  // a vector of 8 channels spans 1 or 2 groups when cpg >= 4
-  for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const uint4 v = base[i];
+  const int g0 = c0 / cpg;  // a vector of 8 channels spans 1 or 2 groups when cpg >= 4
+  int which[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) which[e] = ((c0 + 2 * e) / cpg == g0) ? 0 : 1;
+  auto acc = [&](const uint4& v) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = bf16_lo(u[e]), c = bf16_hi(u[e]);
-      const int which = ((c0 + 2 * e) / cpg == g0) ? 0 : 1;
-      s[which] += a + c;
-      q[which] += a * a + c * c;
+      s[which[e]] += a + c;
+      q[which[e]] += a * a + c * c;
     }
+  };
+  long long i = threadIdx.x;
+  for (; i + 3 * 256 < nvec; i += 4 * 256) {   // four independent loads in flight per thread
+    const uint4 v0 = base[i], v1 = base[i + 256], v2 = base[i + 512], v3 = base[i + 768];
+    acc(v0); acc(v1); acc(v2); acc(v3);
   }
+  for (; i < nvec; i += 256) acc(base[i]);
   part[threadIdx.x] = make_float4(s[0], q[0], s[1], q[1]);
   __syncthreads();
   if (threadIdx.x < G) {
@@ -58,54 +69,76 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part
   }
 }
 
-// pass 2: reduce slabs -> (mean, rstd) per (image, group)
-__global__ void gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int G, int slabs,
-                                   float count, float eps) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
+// pass 2: reduce slabs -> (mean, rstd) per (image, group). 8 threads per group take every 8th slab (fixed assignment),
+// then combine in a fixed order: deterministic, and 8x shorter than a serial walk over up to 1024 slabs.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stats, int G, int slabs, float count,
+                   float eps) {
+  const int b = blockIdx.x, g = threadIdx.x & 31, lane8 = threadIdx.x >> 5;   // G == 32
+  __shared__ double sh_s[8][32], sh_q[8][32];
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < slabs; ++i) {
+  for (int i = lane8; i < slabs; i += 8) {
     const float2 p = partial[((long long)b * slabs + i) * G + g];
     s += p.x;
     q += p.y;
   }
-  const double mean = s / count;
-  const double var = fmax(q / count - mean * mean, 0.0);
-  stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  sh_s[lane8][g] = s;
+  sh_q[lane8][g] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += sh_s[k][g]; q += sh_q[k][g]; }
+    const double mean = s / count;
+    const double var = fmax(q / count - mean * mean, 0.0);
+    stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
 }
 
-// pass 3: y = bf16( act( (x - mean) * rstd * w + b ) ), act = swish (x * sigmoid(x)) or identity
+// pass 3: y = bf16( act( (x - mean) * rstd * w + b ) ), act = swish (x * sigmoid(x)) or identity. A thread owns one
+// 8-channel slot of the pixel (grid stride is a multiple of the vectors per pixel), so its affine parameters and group
+// statistics are loaded ONCE; the loop is load / 8 FMA (+ swish) / store with four vectors in flight.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ w,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long HW, int C, int G,
-                int swish, long long total_vec) {
+                int swish, long long vec_per_image) {
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / vec_per_pix;
-    const int c0 = (int)(i - pix * vec_per_pix) * 8;
-    const int b = (int)(pix / HW);
-    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
-    const float4 w0 = *reinterpret_cast<const float4*>(w + c0), w1 = *reinterpret_cast<const float4*>(w + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
-    const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    const float bf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int b = blockIdx.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;          // multiple of vec_per_pix (256 % vpp == 0)
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i % vec_per_pix) * 8;
+  float sc[8], sh[8];   // y = x * sc + sh  with sc = rstd * w, sh = b - mean * rstd * w  (same value, fewer ops per element:
+                        // (x - mean) * rstd * w + b evaluated as one FMA; fp32, far below the bf16 output rounding)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 st = stats[b * G + (c0 + e) / cpg];
+    const float ww = w[c0 + e];
+    sc[e] = st.y * ww;
+    sh[e] = bias[c0 + e] - st.x * st.y * ww;
+  }
+  const uint4* xi = reinterpret_cast<const uint4*>(x) + (long long)b * vec_per_image;
+  uint4* yo = reinterpret_cast<uint4*>(y) + (long long)b * vec_per_image;
+  auto one = [&](const uint4& v) -> uint4 {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 st0 = stats[b * G + (c0 + 2 * e) / cpg];
-      const float2 st1 = stats[b * G + (c0 + 2 * e + 1) / cpg];
-      float a = (bf16_lo(u[e]) - st0.x) * st0.y * wf[2 * e] + bf[2 * e];
-      float c = (bf16_hi(u[e]) - st1.x) * st1.y * wf[2 * e + 1] + bf[2 * e + 1];
+      float a = fmaf(bf16_lo(u[e]), sc[2 * e], sh[2 * e]);
+      float c = fmaf(bf16_hi(u[e]), sc[2 * e + 1], sh[2 * e + 1]);
       if (swish) {
-        a = a / (1.0f + __expf(-a));
-        c = c / (1.0f + __expf(-c));
+        a = __fdividef(a, 1.0f + __expf(-a));
+        c = __fdividef(c, 1.0f + __expf(-c));
       }
       o[e] = pack_bf16x2(a, c);
     }
-    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  for (; i + 3 * stride < vec_per_image; i += 4 * stride) {
+    const uint4 v0 = xi[i], v1 = xi[i + stride], v2 = xi[i + 2 * stride], v3 = xi[i + 3 * stride];
+    yo[i] = one(v0); yo[i + stride] = one(v1); yo[i + 2 * stride] = one(v2); yo[i + 3 * stride] = one(v3);
   }
+  for (; i < vec_per_image; i += stride) yo[i] = one(xi[i]);
 }
 
 // nearest-neighbour 2x upsample, NHWC: y[b, 2h+i, 2w+j, :] = x[b, h, w, :]
@@ -125,15 +158,28 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   }
 }
 
-// P[r, :] = bf16(softmax(S[r, :] * scale)) — one block per row, fp32 logits (VAE mid attention, d = 512)
+// P[r, :] = bf16(softmax(S[r, :] * scale)) — one block per row, fp32 logits (VAE mid attention, d = 512).
+// kPer > 0: the row (L <= 256 * kPer) is read ONCE into registers (max, sum and output from the same values: 1 read +
+// 1 bf16 write instead of three fp32 passes); kPer = 0: any L, three passes.
+template <int kPer>
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P, long long ldp, int L,
                     float scale_log2) {
   const long long r = blockIdx.x;
   const float* s = S + r * lds;
   __shared__ float red[8];
+  float v[kPer > 0 ? kPer : 1];
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, s[i]);
+  if constexpr (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = threadIdx.x + k * 256;
+      v[k] = (i < L) ? s[i] : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, s[i]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -143,7 +189,15 @@ softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* _
   for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) sum += exp2f((s[i] - mx) * scale_log2);
+  if constexpr (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      v[k] = exp2f((v[k] - mx) * scale_log2);     // -inf padding -> 0
+      sum += v[k];
+    }
+  } else {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) sum += exp2f((s[i] - mx) * scale_log2);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -153,7 +207,15 @@ softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* _
   for (int i = 0; i < 8; ++i) sum += red[i];
   const float inv = 1.0f / sum;
   __nv_bfloat16* p = P + r * ldp;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) p[i] = __float2bfloat16_rn(exp2f((s[i] - mx) * scale_log2) * inv);
+  if constexpr (kPer > 0) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < L) p[i] = __float2bfloat16_rn(v[k] * inv);
+    }
+  } else {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) p[i] = __float2bfloat16_rn(exp2f((s[i] - mx) * scale_log2) * inv);
+  }
 }
 
 // y[c, r] = x[r, c]  (bf16, 32x32 smem tiles)
@@ -179,8 +241,7 @@ using namespace bagel;
 #define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 extern "C" long long bagel_groupnorm_workspace_bytes(int B, int groups) {
-  const int slabs = 64;
-  return (long long)B * slabs * groups * sizeof(float2) + (long long)B * groups * sizeof(float2);
+  return (long long)B * kGnMaxSlabs * groups * sizeof(float2) + (long long)B * groups * sizeof(float2);
 }
 
 extern "C" int bagel_groupnorm_nhwc_bf16(const void* x, const void* w, const void* b, void* y, void* workspace, int B,
@@ -191,20 +252,26 @@ extern "C" int bagel_groupnorm_nhwc_bf16(const void* x, const void* w, const voi
   if (C % 128 || (256 % vpp) != 0) return set_error(BAGEL_ERR_SHAPE, "bagel_groupnorm_nhwc_bf16: C must be 128, 256 or 512");
   if (workspace == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_groupnorm_nhwc_bf16: workspace required");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int slabs = 64;
-  if (HW < slabs) slabs = (int)HW;
+  // enough slabs for ~8 CTAs per SM over the batch, at least 64 pixels per slab, at most kGnMaxSlabs (workspace size)
+  long long want = (148LL * 8 + B - 1) / B;
+  if (want > HW / 64) want = HW / 64;
+  if (want > kGnMaxSlabs) want = kGnMaxSlabs;
+  if (want < 1) want = 1;
+  const int slabs = (int)want;
   float2* partial = static_cast<float2*>(workspace);
-  float2* stats = partial + (long long)B * 64 * groups;
+  float2* stats = partial + (long long)B * kGnMaxSlabs * groups;
   auto X = static_cast<const __nv_bfloat16*>(x);
   gn_partial_kernel<<<dim3(slabs, B), 256, 0, s>>>(X, partial, HW, C, groups, slabs);
   COUNT_LAUNCH();
-  gn_finalize_kernel<<<B, 32, 0, s>>>(partial, stats, groups, slabs, (float)((double)HW * (C / groups)), eps);
+  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, stats, groups, slabs, (float)((double)HW * (C / groups)), eps);
   COUNT_LAUNCH();
-  const long long total_vec = (long long)B * HW * vpp;
-  long long blocks = (total_vec + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<(unsigned)blocks, 256, 0, s>>>(X, stats, static_cast<const float*>(w), static_cast<const float*>(b),
-                                                     static_cast<__nv_bfloat16*>(y), HW, C, groups, swish, total_vec);
+  const long long vec_per_image = HW * vpp;
+  long long blocks = (vec_per_image + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (148LL * 16 + B - 1) / B;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  gn_apply_kernel<<<dim3((unsigned)blocks, B), 256, 0, s>>>(X, stats, static_cast<const float*>(w), static_cast<const float*>(b),
+                                                            static_cast<__nv_bfloat16*>(y), HW, C, groups, swish, vec_per_image);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -226,8 +293,13 @@ extern "C" int bagel_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, 
 extern "C" int bagel_softmax_rows_f32(const float* S, long long lds, void* P, long long ldp, int rows, int L,
                                       float scale, void* stream) {
   if (rows <= 0 || L <= 0) return 0;
-  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, static_cast<__nv_bfloat16*>(P), ldp, L,
-                                                                          scale * 1.4426950408889634f);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto Pb = static_cast<__nv_bfloat16*>(P);
+  const float sl2 = scale * 1.4426950408889634f;
+  if (L <= 256 * 8) softmax_rows_kernel<8><<<rows, 256, 0, st>>>(S, lds, Pb, ldp, L, sl2);
+  else if (L <= 256 * 32) softmax_rows_kernel<32><<<rows, 256, 0, st>>>(S, lds, Pb, ldp, L, sl2);
+  else if (L <= 256 * 64) softmax_rows_kernel<64><<<rows, 256, 0, st>>>(S, lds, Pb, ldp, L, sl2);
+  else softmax_rows_kernel<0><<<rows, 256, 0, st>>>(S, lds, Pb, ldp, L, sl2);
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -351,7 +351,7 @@ def main():
     flops_launch = 2.0 * rows * (2 * cfg.intermediate_size) * cfg.hidden_size
     roof = None
     traffic, traffic_src = None, None
-    prof = os.path.join(ROOT, "profiles", "r01_gemm_swiglu_ncu_full.csv")
+    prof = os.path.join(ROOT, "profiles", "r02_gemm2_swiglu_ncu_full.csv")
     if os.path.exists(prof) and rows == 65568:   # the capture was taken on exactly this launch shape
         try:
             vals = {}
@@ -360,14 +360,15 @@ def main():
                     name, unit, v = [x.strip().strip('"') for x in ln.split(",")]
                     vals[name] = float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
             traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-            traffic_src = "profiles/r01_gemm_swiglu_ncu_full.csv (ncu --set full, one launch of this kernel/shape)"
+            traffic_src = "profiles/r02_gemm2_swiglu_ncu_full.csv (ncu --set full, one launch of this kernel/shape, this build)"
         except Exception:
             traffic = None
     if swiglu_ms:
         avg_ms = statistics.mean(swiglu_ms)
         ach = flops_launch / (avg_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-        roof = {"kernel": "gemm_bf16_kernel<256,SWIGLU> (gate|up projection + SiLU*up epilogue)", "bound": "tensor",
+        roof = {"kernel": "gemm2_bf16_kernel<SWIGLU> (CTA-pair tcgen05 cta_group::2; gate|up projection + SiLU*up epilogue)",
+                "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_unit": "bytes/launch (dram read+write)", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": 2.0 * (rows * cfg.hidden_size + 2 * cfg.intermediate_size * cfg.hidden_size
