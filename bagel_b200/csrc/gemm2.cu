@@ -60,6 +60,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool leader = rank == 0;
   const int num_k = (p.K + BK - 1) / BK;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int nstages = p.stages;   // <= kStages
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -98,7 +99,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_2d_2sm(smem_a + stage * kPairABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM, hint_a);
           tma_load_2d_2sm(smem_b + stage * kPairBBytes, &tmB, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * kPairBNH,
                           hint_w);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -122,7 +123,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           umma_commit_2sm_mc(&empty_bar[stage], 0b11);  // slot reusable in both CTAs once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm_mc(&tfull_bar[acc], 0b11);  // accumulator complete -> epilogue warps of both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -267,6 +268,8 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     if (gn <= 0 || gn > p.num_n) gn = p.num_n;
     p.group_n = gn;
     p.hints = env_h >= 0 ? env_h : 0;
+    static const int env_s = [] { const char* e = getenv("BAGEL_GEMM_PAIR_STAGES"); return e ? atoi(e) : 0; }();
+    p.stages = (env_s >= 2 && env_s <= kPairStages) ? env_s : kPairStages;
   }
   switch (epilogue) {
     case EPI_BIAS: return launch2<EPI_BIAS>(tmA, tmB, p, stream);

@@ -33,18 +33,19 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part
   // vec_per_pix in {16,32,64}), so its channels -> groups mapping is fixed
   const int slot = threadIdx.x % vec_per_pix;
   const int c0 = slot * 8;
-  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   const int g0 = c0 / cpg;  // a vector of 8 channels spans 1 or 2 groups when cpg >= 4
-  int which[4];
+  float m0[4];              // 1 if channel pair e belongs to the vector's first group, else 0 (no dynamic register indexing)
 #pragma unroll
-  for (int e = 0; e < 4; ++e) which[e] = ((c0 + 2 * e) / cpg == g0) ? 0 : 1;
+  for (int e = 0; e < 4; ++e) m0[e] = ((c0 + 2 * e) / cpg == g0) ? 1.0f : 0.0f;
   auto acc = [&](const uint4& v) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float a = bf16_lo(u[e]), c = bf16_hi(u[e]);
-      s[which[e]] += a + c;
-      q[which[e]] += a * a + c * c;
+      const float sm = a + c, sq = fmaf(a, a, c * c);
+      s0 = fmaf(m0[e], sm, s0); q0 = fmaf(m0[e], sq, q0);
+      s1 = fmaf(1.0f - m0[e], sm, s1); q1 = fmaf(1.0f - m0[e], sq, q1);
     }
   };
   long long i = threadIdx.x;
@@ -53,7 +54,7 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part
     acc(v0); acc(v1); acc(v2); acc(v3);
   }
   for (; i < nvec; i += 256) acc(base[i]);
-  part[threadIdx.x] = make_float4(s[0], q[0], s[1], q[1]);
+  part[threadIdx.x] = make_float4(s0, q0, s1, q1);
   __syncthreads();
   if (threadIdx.x < G) {
     const int g = threadIdx.x;
@@ -77,7 +78,13 @@ gn_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ stat
   const int b = blockIdx.x, g = threadIdx.x & 31, lane8 = threadIdx.x >> 5;   // G == 32
   __shared__ double sh_s[8][32], sh_q[8][32];
   double s = 0.0, q = 0.0;
-  for (int i = lane8; i < slabs; i += 8) {
+  int i = lane8;
+  for (; i + 24 < slabs; i += 32) {   // four independent loads in flight
+    const float2 p0 = partial[((long long)b * slabs + i) * G + g], p1 = partial[((long long)b * slabs + i + 8) * G + g];
+    const float2 p2 = partial[((long long)b * slabs + i + 16) * G + g], p3 = partial[((long long)b * slabs + i + 24) * G + g];
+    s += p0.x; q += p0.y; s += p1.x; q += p1.y; s += p2.x; q += p2.y; s += p3.x; q += p3.y;
+  }
+  for (; i < slabs; i += 8) {
     const float2 p = partial[((long long)b * slabs + i) * G + g];
     s += p.x;
     q += p.y;
@@ -252,8 +259,8 @@ extern "C" int bagel_groupnorm_nhwc_bf16(const void* x, const void* w, const voi
   if (C % 128 || (256 % vpp) != 0) return set_error(BAGEL_ERR_SHAPE, "bagel_groupnorm_nhwc_bf16: C must be 128, 256 or 512");
   if (workspace == nullptr) return set_error(BAGEL_ERR_ARG, "bagel_groupnorm_nhwc_bf16: workspace required");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // enough slabs for ~8 CTAs per SM over the batch, at least 64 pixels per slab, at most kGnMaxSlabs (workspace size)
-  long long want = (148LL * 8 + B - 1) / B;
+  // enough slabs for ~4 CTAs per SM over the batch, at least 64 pixels per slab, at most kGnMaxSlabs (workspace size)
+  long long want = (148LL * 4 + B - 1) / B;
   if (want > HW / 64) want = HW / 64;
   if (want > kGnMaxSlabs) want = kGnMaxSlabs;
   if (want < 1) want = 1;
