@@ -5,7 +5,8 @@
 // shared-memory traffic and 48 KB of shared-memory reads per 128x256x64 MMA block). A CTA PAIR (two CTAs of a 2-CTA
 // cluster on one TPC, tcgen05 `cta_group::2`) computes a 256 x 256 tile with ONE MMA stream: each CTA stages its own 128
 // rows of A and only HALF of the W tile (128 of the 256 rows), the tensor cores of both SMs read both halves. Per CTA and
-// K block that is 32 KB instead of 48 KB (-33 % L2->smem and smem->tensor-core bytes), and the ring gets 6 stages deep.
+// K block that is 32 KB instead of 48 KB (-33 % L2->smem and smem->tensor-core bytes). The smem ring has room for 6 stages;
+// 4 are used (see gemm2_launch: prefetching deeper costs more in L2 misses than it hides).
 //
 //   warp 0 (both CTAs)   TMA producer: A tile [128 x 64] of its M half, W half-tile [128 x 64]; every load completes on
 //                        the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2, peer bit cleared)
@@ -269,7 +270,11 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     p.group_n = gn;
     p.hints = env_h >= 0 ? env_h : 0;
     static const int env_s = [] { const char* e = getenv("BAGEL_GEMM_PAIR_STAGES"); return e ? atoi(e) : 0; }();
-    p.stages = (env_s >= 2 && env_s <= kPairStages) ? env_s : kPairStages;
+    // FOUR stages in use although six fit: with a deeper ring the 74 pairs prefetch so far ahead that the A panel of the
+    // raster group no longer survives in the L2 between its reuses — DRAM reads 8.6-24 GB per gate|up launch with 6 stages,
+    // 11.4 GB with 5, 5.1 GB with 4 (= the compulsory 16 x W + 1 x A of this raster), and the power-capped step follows the
+    // DRAM bytes: 813 / 785 / 782 ms (profiles/r02_gemm_pair_ab.txt). Three stages starve the tensor pipe (841 ms).
+    p.stages = (env_s >= 2 && env_s <= kPairStages) ? env_s : 4;
   }
   switch (epilogue) {
     case EPI_BIAS: return launch2<EPI_BIAS>(tmA, tmB, p, stream);

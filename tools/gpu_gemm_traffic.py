@@ -2,8 +2,8 @@
 the power-capped denoising step (bench.py --steps 8). One process per setting."""
 import os, subprocess, sys, json
 # (pair, group_m in M-tiles, group_n, hints, pair stages)
-cfgs = [("0", "0", "0", "0", "0"), ("0", "32", "0", "0", "0"), ("1", "32", "0", "0", "0"), ("1", "32", "0", "0", "4"), ("1", "32", "0", "0", "3"),
-        ("1", "16", "0", "0", "4"), ("1", "8", "0", "0", "0"), ("1", "32", "0", "8", "4")]
+cfgs = [("1", "32", "0", "0", "4"), ("1", "32", "0", "8", "4"), ("1", "48", "0", "8", "4"), ("1", "64", "0", "8", "4"), ("1", "64", "0", "0", "4"),
+        ("1", "32", "37", "9", "4"), ("1", "32", "0", "8", "5"), ("1", "32", "0", "12", "4"), ("1", "32", "0", "8", "4")]
 M = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct"
 for pr, gm, gn, h, st in cfgs:
     env = dict(os.environ, BAGEL_GEMM_PAIR=pr, BAGEL_GEMM_GROUP_M=gm, BAGEL_GEMM_GROUP_N=gn, BAGEL_GEMM_HINTS=h, BAGEL_GEMM_PAIR_STAGES=st)
