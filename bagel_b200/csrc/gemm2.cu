@@ -265,10 +265,20 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     // one box (profiles/r02_gemm_pair_ab.txt): groups of 16 pairs (32 M tiles: W is streamed from DRAM 16x instead of 32x
     // per launch, the 29 MB A panel of a group stays L2-resident) 809-811 ms per step, 8 pairs 836 ms, 1-CTA kernel 816 ms.
     p.group_m = env_g > 0 ? (env_g + 1) / 2 : 16;
+    // Large K (down_proj, K = 18944): the A panel of 16 pairs is 155 MB and cannot stay in the L2 between the sweeps over
+    // the N tiles. A/B knobs for such GEMMs (K > 8192): BAGEL_GEMM_BIGK = "group_pairs,group_n,hints".
+    static int bk_gp = 0, bk_gn = 0, bk_h = 0;
+    static const bool bk_set = [] {
+      const char* e = getenv("BAGEL_GEMM_BIGK");
+      return e && sscanf(e, "%d,%d,%d", &bk_gp, &bk_gn, &bk_h) == 3;
+    }();
+    const bool bigk = bk_set && p.K > 8192;
+    if (bigk && bk_gp > 0) p.group_m = bk_gp;
     int gn = env_n >= 0 ? env_n : 0;
+    if (bigk) gn = bk_gn;
     if (gn <= 0 || gn > p.num_n) gn = p.num_n;
     p.group_n = gn;
-    p.hints = env_h >= 0 ? env_h : 0;
+    p.hints = bigk ? bk_h : (env_h >= 0 ? env_h : 0);
     static const int env_s = [] { const char* e = getenv("BAGEL_GEMM_PAIR_STAGES"); return e ? atoi(e) : 0; }();
     // FOUR stages in use although six fit: with a deeper ring the 74 pairs prefetch so far ahead that the A panel of the
     // raster group no longer survives in the L2 between its reuses — DRAM reads 8.6-24 GB per gate|up launch with 6 stages,
