@@ -83,6 +83,26 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
   return 0;
 }
 
+// Store-side map: box [box_rows, box_cols] with box_cols * 2 == 64 bytes and 64-byte swizzle (the epilogue warps stage
+// 32 x 32 bf16 sub-tiles: the 16-byte chunk index of a row is XORed with (row >> 1) & 3, which makes their 16-byte
+// shared-memory writes conflict-free). Rows / columns beyond the tensor are clipped by the TMA unit.
+int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                            uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(BAGEL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(BAGEL_ERR_CUDA, "cuTensorMapEncodeTiled(store) failed (%d) base=%p cols=%llu rows=%llu ld=%llu", (int)r,
+                     base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
+  return 0;
+}
+
 int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
                            uint32_t box_w, uint32_t box_h, uint32_t stride) {
   EncodeTiledFn fn = encode_fn();

@@ -13,7 +13,8 @@
 //   warp 1 (leader)      one lane issues tcgen05.mma.cta_group::2 (M 256, N 256, K 16) — fp32 accumulators: 128 rows x
 //                        256 columns in EACH CTA's TMEM, two stages; tcgen05.commit ... multicast frees the smem slot in
 //                        both CTAs / hands the accumulator to both epilogues
-//   warps 2..5 (both)    epilogue of the CTA's own 128 rows: tcgen05.ld -> fused bias / residual / SwiGLU -> global;
+//   warps 2..5 (both)    epilogue of the CTA's own 128 rows: tcgen05.ld -> fused bias / residual / SwiGLU -> 32x32 sub-tiles
+//                        staged in (swizzled) shared memory -> cp.async.bulk.tensor stores (direct stores with row_map);
 //                        both CTAs' warps arrive on the leader's "accumulator drained" barrier
 // Reference ops replaced: the same nn.Linear calls as gemm.cu (modeling/bagel/qwen2_navit.py:589-594,
 // modeling/qwen2/modeling_qwen2.py:200-201) — this kernel is selected by bagel_gemm_bf16 for large M.
@@ -36,11 +37,13 @@ constexpr int kPairStages = 6;
 constexpr int kPairABytes = BM * BK * 2;        // 16 KB
 constexpr int kPairBBytes = kPairBNH * BK * 2;  // 16 KB
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+constexpr int kPairStgBytes = 4 * 2 * 2048;   // epilogue staging for TMA stores: 4 warps x 2 buffers x [32 rows x 32 bf16]
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairStgBytes + 1024 + 256;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr int BN = kPairBN;
   constexpr int kStages = kPairStages;
   extern __shared__ uint8_t smem_raw[];
@@ -48,7 +51,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kPairABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kPairStageBytes);
+  uint8_t* smem_stg = smem + kStages * kPairStageBytes;   // 1024-byte aligned (64-byte swizzle atoms are 512 bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kPairStgBytes);
   uint64_t* full_bar = bars;                 // [kStages]  TMA (both CTAs) -> MMA        (leader's copy is used)
   uint64_t* empty_bar = bars + kStages;      // [kStages]  MMA -> TMA                    (each CTA its own, multicast arrive)
   uint64_t* tfull_bar = bars + 2 * kStages;  // [2]        MMA -> epilogue               (each CTA its own, multicast arrive)
@@ -66,6 +70,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);   // the leader's arrive.expect_tx (bytes of BOTH CTAs)
       mbar_init(&empty_bar[i], 1);  // one multicast commit
@@ -135,6 +140,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const bool streaming = (p.hints & 4) != 0;
+    const bool tma_out = p.tma_store != 0;
+    uint8_t* stg = smem_stg + quarter * 4096;   // this warp's two 2 KB staging buffers
+    int stg_buf = 0;
+    // One 32-row x 32-column bf16 sub-tile of C: registers -> swizzled shared memory -> ONE bulk tensor store issued by lane 0
+    // (full 64-byte row segments leave the SM as whole sectors instead of 32 scattered 16-byte stores per instruction; rows
+    // past M are clipped by the TMA unit). The buffer is reused two stores later: wait until that store has READ it.
+    auto store_tile_tma = [&](const uint32_t (&o)[16], int col0, int row0) {
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      uint8_t* b = stg + stg_buf * 2048;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(b + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmC, b, col0, row0);
+        tma_store_commit();
+      }
+      stg_buf ^= 1;
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
@@ -160,7 +187,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld_x32(t_acc + c * 32, g);
           tmem_ld_x32(t_acc + 128 + c * 32, u);
           tmem_ld_wait();
-          if (row_ok) {
+          if (row_ok || tma_out) {
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -168,9 +195,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const float g1 = bf16_round(__uint_as_float(g[2 * j + 1])), u1 = bf16_round(__uint_as_float(u[2 * j + 1]));
               o[j] = pack_bf16x2(bf16_round(silu_f(g0)) * u0, bf16_round(silu_f(g1)) * u1);
             }
-            uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);   // N % 256 == 0: always a full chunk
+            if (tma_out) {
+              store_tile_tma(o, n_out0 + c * 32, (2 * mp + (int)rank) * BM + quarter * 32);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);   // N % 256 == 0: always a full chunk
 #pragma unroll
-            for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), streaming);
+              for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), streaming);
+            }
           }
         }
       } else {
@@ -182,14 +213,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t v[32];
           tmem_ld_x32(t_acc + c * 32, v);
           tmem_ld_wait();
-          if (row_ok) {
+          if (row_ok || tma_out) {
             uint32_t rr[16];
             if constexpr (EPI == EPI_RESID) {
-              const uint4* src = reinterpret_cast<const uint4*>(rrow + c * 32);
+              if (row_ok) {
+                const uint4* src = reinterpret_cast<const uint4*>(rrow + c * 32);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 t = src[q];
-                rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 t = src[q];
+                  rr[4 * q] = t.x; rr[4 * q + 1] = t.y; rr[4 * q + 2] = t.z; rr[4 * q + 3] = t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) rr[j] = 0u;   // rows past M: computed but clipped by the TMA store
               }
             }
             uint32_t o[16];
@@ -208,9 +244,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
               o[j] = pack_bf16x2(x0, x1);
             }
-            uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);   // N % 256 == 0: always a full chunk
+            if (tma_out) {
+              store_tile_tma(o, n0_tile + c * 32, (2 * mp + (int)rank) * BM + quarter * 32);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);   // N % 256 == 0: always a full chunk
 #pragma unroll
-            for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), streaming);
+              for (int q = 0; q < 4; ++q) store16(dst + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]), streaming);
+            }
           }
         }
       }
@@ -219,6 +259,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's barrier counts both CTAs' epilogue warps
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tma_out && lane == 0) tma_store_wait<0>();   // the staging buffers must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -231,7 +272,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int EPI>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                   cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<EPI>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -240,7 +282,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPar
   }
   int clusters = sm_count() / 2;
   if (clusters > p.num_tiles) clusters = p.num_tiles;
-  kern<<<2 * clusters, kGemmThreads, kPairSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<2 * clusters, kGemmThreads, kPairSmemBytes, stream>>>(tmA, tmB, tmC, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BAGEL_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -286,10 +328,18 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     // DRAM bytes: 813 / 785 / 782 ms (profiles/r02_gemm_pair_ab.txt). Three stages starve the tensor pipe (841 ms).
     p.stages = (env_s >= 2 && env_s <= kPairStages) ? env_s : 4;
   }
+  // epilogue through shared memory + bulk tensor stores unless the output rows are scattered (row_map)
+  static const bool tma_store_on = [] { const char* e = getenv("BAGEL_GEMM_TMA_STORE"); return !(e && atoi(e) == 0); }();
+  p.tma_store = (tma_store_on && p.row_map == nullptr) ? 1 : 0;
+  CUtensorMap tmC{};
+  if (p.tma_store) {
+    const uint64_t out_cols = epilogue == EPI_SWIGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
+    if (int rc = make_tmap_2d_bf16_store(&tmC, p.C, out_cols, (uint64_t)p.M, (uint64_t)p.ldc, 32, 32)) return rc;
+  }
   switch (epilogue) {
-    case EPI_BIAS: return launch2<EPI_BIAS>(tmA, tmB, p, stream);
-    case EPI_RESID: return launch2<EPI_RESID>(tmA, tmB, p, stream);
-    case EPI_SWIGLU: return launch2<EPI_SWIGLU>(tmA, tmB, p, stream);
+    case EPI_BIAS: return launch2<EPI_BIAS>(tmA, tmB, tmC, p, stream);
+    case EPI_RESID: return launch2<EPI_RESID>(tmA, tmB, tmC, p, stream);
+    case EPI_SWIGLU: return launch2<EPI_SWIGLU>(tmA, tmB, tmC, p, stream);
     default: return set_error(BAGEL_ERR_ARG, "gemm2: unsupported epilogue %d", epilogue);
   }
 }

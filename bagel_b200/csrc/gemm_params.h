@@ -49,6 +49,7 @@ struct GemmParams {
   int num_m, num_n, num_tiles;
   int group_m;  // rasterisation: group_m M-tiles share one sweep over the N tiles (their A panels stay in L2)
   int group_n;  // N super-tiles: all M groups sweep group_n N-tiles before the next group_n (that W sub-panel stays in L2)
+  int tma_store;  // CTA-pair kernel: epilogue writes C through shared memory + cp.async.bulk.tensor stores (no row_map)
   int stages;   // CTA-pair kernel: smem ring stages actually used (<= compile-time depth; A/B knob)
   int hints;    // L2 policy bits: 1 W evict_last, 2 A evict_first, 4 streaming (evict-first) output stores, 8 A evict_last,
                 // 16 W evict_first

@@ -21,6 +21,10 @@ int require_sm100();                            // 0 if current device is sm_100
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows);
 
+// 2D bf16 tensor map for TMA STORES of [box_rows, box_cols] sub-tiles (box_cols * 2 = 64 bytes, 64-byte swizzle).
+int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                            uint32_t box_cols, uint32_t box_rows);
+
 // 4-D bf16 tensor map over an NHWC activation [B, H, W, C]: box [1, box_h, box_w, box_c] output pixels, traversal
 // stride `stride` along W and H (strided convolutions), 128-byte swizzle, zero fill outside the tensor.
 int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,

@@ -356,7 +356,7 @@ def main():
         try:
             vals = {}
             for ln in open(prof):
-                if ln.startswith('"dram__bytes_'):
+                if ln.startswith('"dram__bytes_read.sum",') or ln.startswith('"dram__bytes_write.sum",'):
                     name, unit, v = [x.strip().strip('"') for x in ln.split(",")]
                     vals[name] = float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
             traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
