@@ -33,6 +33,19 @@
 
 namespace bagel {
 
+// Optional timeline instrumentation (tools/gpu_attn_trace.py builds a separate library with -DBAGEL_ATTN_TRACE; the product
+// library never defines it): CTA 0 records clock64() stamps of the softmax warps 0 / 4 and the MMA lane for its first blocks.
+#ifdef BAGEL_ATTN_TRACE
+constexpr int kTraceIters = 1024, kTraceEvents = 8;
+__device__ long long g_attn_trace[3 * kTraceIters * kTraceEvents];
+#define ATTN_TRACE(role, iter, ev)                                                                   \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (iter) < kTraceIters) g_attn_trace[((role) * kTraceIters + (iter)) * kTraceEvents + (ev)] = clock64(); \
+  } while (0)
+#else
+#define ATTN_TRACE(role, iter, ev) do { } while (0)
+#endif
+
 constexpr int kAttnThreads = (8 + 2) * 32;  // softmax warps of both tiles (4 + 4) + TMA warp + MMA warp
 constexpr int kBlockM = 128;  // rows per query tile (2 tiles per work item)
 constexpr int kBlockN = 128;  // keys per block
@@ -241,6 +254,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t icnt[2] = {0, 0};    // items processed per tile (parity of o_free)
       int slot = 0;
       uint32_t sphase = 0;
+      [[maybe_unused]] int tr_it = 0;
 
       auto issue_qk = [&](int t, int kstage) {
         // K-major operands: D columns = kAtoms atoms of 64; 4 UMMA_K=16 steps per atom (+32 B each)
@@ -300,7 +314,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int t = 0; t < ntile; ++t) {
             if (j >= w.nblk_t[t]) continue;      // causal: this block lies entirely above the tile's diagonal
             const bool t_next = (j + 1) < w.nblk_t[t];
+            ATTN_TRACE(2, tr_it, 0);
             mbar_wait(&p_bar[t], pcnt[t] & 1);  // P_t(j) in TMEM, O_t rescaled
+            ATTN_TRACE(2, tr_it, 1);
             ++pcnt[t];
             if (j == 0) mbar_wait(&o_free[t], (icnt[t] & 1) ^ 1);   // the previous item's O_t has been read out
             tc_fence_after();
@@ -308,6 +324,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (!t_next) umma_commit(&o_bar[t]);
             // S_t(j+1) overwrites the columns P_t(j) lives in: safe because the tensor pipe executes in issue order
             if (t_next) issue_qk(t, kstage);
+            ATTN_TRACE(2, tr_it, 2);
+#ifdef BAGEL_ATTN_TRACE
+            if (blockIdx.x == 0 && tr_it < kTraceIters) g_attn_trace[(2 * kTraceIters + tr_it) * kTraceEvents + 3] = t;
+            ++tr_it;
+#endif
           }
           umma_commit(&kv_empty[vstage]);
           if (has_next) umma_commit(&kv_empty[kstage]);
@@ -331,6 +352,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t icnt = 0;     // items processed by this tile (parity of o_bar)
     int slot = 0;
     uint32_t sphase = 0;
+    [[maybe_unused]] int tr_it = 0;
+    [[maybe_unused]] const bool tr_on = (quarter == 0 && lane == 0);
 
     while (true) {
       mbar_wait(&sched_full[slot], sphase);
@@ -359,7 +382,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // (or overflowed: inf / NaN fail the comparison too). Exercised by tests/test_gpu_attn_adversarial.py.
       constexpr float kRedoSum = 1073741824.0f;   // 2^30
       for (int j = 0; j < nblk; ++j) {
+        if (tr_on) ATTN_TRACE(t, tr_it, 0);
         mbar_wait(&s_bar[t], scnt & 1);
+        if (tr_on) ATTN_TRACE(t, tr_it, 1);
         ++scnt;
         tc_fence_after();
         const int kv0 = j * kBlockN;               // first key of this block
@@ -415,6 +440,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           else stream(std::false_type{});
           const float rs_row = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
           redo = !(rs_row <= kRedoSum);
+          if (tr_on) ATTN_TRACE(t, tr_it, 2);
         }
         float alpha = 1.0f;
         if (__any_sync(0xffffffffu, redo)) {
@@ -472,9 +498,14 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int c = 0; c < NC / 64; ++c)
           tmem_st_x32(tP + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]));
         tmem_st_wait();
+        if (tr_on) ATTN_TRACE(t, tr_it, 3);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_bar[t]);
+        if (tr_on) ATTN_TRACE(t, tr_it, 4);
+#ifdef BAGEL_ATTN_TRACE
+        ++tr_it;
+#endif
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
@@ -570,6 +601,13 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
 }  // namespace bagel
 
 using namespace bagel;
+
+#ifdef BAGEL_ATTN_TRACE
+extern "C" int bagel_attn_trace_read(long long* host, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * n);
+}
+#endif
 
 extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v, void* out, const int* cu_seqlens_q,
                                      const int* cu_seqlens_k, int total_q, int total_k, int batch, int num_heads_q,
