@@ -16,6 +16,7 @@ def build():
     sys.path.insert(0, str(ROOT))
     from bagel_b200 import build as bb
     bb.build()
+    OUT.parent.mkdir(parents=True, exist_ok=True)
     obj = OUT.parent / "attn_trace.o"
     subprocess.check_call([bb._nvcc(), *bb.NVCC_FLAGS, "-DBAGEL_ATTN_TRACE", "-c", str(bb.CSRC / "attn.cu"), "-o", str(obj)])
     objs = [str(o) for o in sorted((bb.PKG_DIR / "build").glob("*.o")) if o.name != "attn.o"] + [str(obj)]

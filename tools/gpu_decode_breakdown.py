@@ -1,4 +1,4 @@
-"""Per-kernel breakdown of one text-decode step (run under `ncu --metrics gpu__time_duration.sum`)."""
+"""Per-kernel breakdown of one text-decode step (run under `ncu --profile-from-start off --metrics gpu__time_duration.sum`)."""
 import sys, torch
 sys.path.insert(0, ".")
 from bagel_b200 import synthetic
@@ -13,6 +13,8 @@ cache = model.forward_cache_update_text(NaiveCache(layers), **gi)
 gs = model.prepare_start_tokens(kv, rp, synthetic.NEW_TOKEN_IDS)
 torch.cuda.synchronize()
 print("DECODE_BEGIN", flush=True)
+torch.cuda.profiler.start()
 toks = model.generate_text(past_key_values=cache, max_length=3, do_sample=False, **gs)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("DECODE_END", toks.shape, flush=True)
