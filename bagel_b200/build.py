@@ -76,10 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("bagel_b200: CUDA build failed")
-    link = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = objdir / (LIB_PATH.name + ".tmp")   # link beside the objects, then rename: a reader never sees a partial library
+    link = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"bagel_b200: link failed:\n{r.stdout}")
+    os.replace(tmp, LIB_PATH)
     STAMP.write_text(_digest())
     return LIB_PATH
 

@@ -41,6 +41,11 @@ static const DevInfo& dev_info() {
 
 int sm_count() { return dev_info().sms; }
 
+bool pdl_small_enabled() {
+  static const bool on = [] { const char* e = getenv("BAGEL_PDL_SMALL"); return e && atoi(e) != 0; }();
+  return on;
+}
+
 int require_sm100() {
   const DevInfo& d = dev_info();
   if (d.major != 10)

@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "attn_decode.h"
+#include "attn3.h"
 
 namespace bagel {
 
@@ -634,6 +635,10 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   const uint64_t rows_k = total_k > 0 ? (uint64_t)total_k : 1;
   if (int rc = make_tmap_2d_bf16(&tmK, k, (uint64_t)num_heads_k * head_dim, rows_k, (uint64_t)ld_k, 64, kBlockN)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmV, v, (uint64_t)num_heads_k * head_dim, rows_k, (uint64_t)ld_v, 64, kBlockN)) return rc;
+
+  if (attn3_enabled())
+    return attn3_varlen(tmQ, tmK, tmV, out, ld_out, cu_seqlens_q, cu_seqlens_k, seqused_k, batch, num_heads_q, num_heads_k,
+                        head_dim, max_seqlen_q, causal, softmax_scale * 1.4426950408889634f, static_cast<cudaStream_t>(stream));
 
   AttnParams p{};
   p.out = static_cast<__nv_bfloat16*>(out);

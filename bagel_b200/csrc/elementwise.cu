@@ -29,38 +29,55 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
                const __nv_bfloat16* __restrict__ w1, const uint8_t* __restrict__ expert,
                __nv_bfloat16* __restrict__ y, long long ldy, int N, int H, float eps) {
   pdl_launch_dependents();   // a following PDL kernel (skinny GEMM) may begin prefetching its weights
+  pdl_wait();                // no-op unless this kernel itself was launched with the PDL attribute (BAGEL_PDL_SMALL)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int nvec = H >> 3;
+  const bool gen = (expert != nullptr && w1 != nullptr) ? (expert[row] != 0) : false;   // in flight with the row loads
   const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  // All loads of the row are issued back to back (select, not branch: with a guarded block per vector the compiler
+  // serialises load -> use -> next load, 14 dependent L2 round trips = 14 us for a 32-row decode call), and the norm
+  // weights are fetched before the reduction rather than after it.
+  constexpr bool kPreW = VPL <= 16;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   uint4 v[VPL];
-  float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      v[i] = xr[idx];
-      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    v[i] = (idx < nvec) ? __ldg(xr + idx) : zero;
+  }
+  const uint4* wr = reinterpret_cast<const uint4*>(gen ? w1 : w0);
+  uint4 wv[kPreW ? VPL : 1];
+  if constexpr (kPreW) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float a = bf16_lo(u[e]), b = bf16_hi(u[e]);
-        ss += a * a + b * b;
-      }
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      wv[i] = (idx < nvec) ? __ldg(wr + idx) : zero;
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = bf16_lo(u[e]), b = bf16_hi(u[e]);
+      ss += a * a + b * b;
     }
   }
   ss = warp_sum(ss);
   const float r = rsqrtf(ss / (float)H + eps);
-  const __nv_bfloat16* w = (expert != nullptr && w1 != nullptr && expert[row]) ? w1 : w0;
-  const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nvec) {
-      const uint4 wv = wr[idx];
+      uint4 wq;
+      if constexpr (kPreW) wq = wv[i];
+      else wq = __ldg(wr + idx);
       const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -173,6 +190,8 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, con
                     __nv_bfloat16* __restrict__ q_out, long long ld_q, __nv_bfloat16* __restrict__ k_out,
                     __nv_bfloat16* __restrict__ v_out, long long ld_kv, const int* __restrict__ kv_rows, int N,
                     int Hq, int Hk, float eps, int fp32_flow) {
+  pdl_launch_dependents();
+  pdl_wait();   // no-op unless launched with the PDL attribute (BAGEL_PDL_SMALL)
   constexpr int E = D / 64;  // elements per lane in each half
   constexpr int HALF = D / 2;
   const int row = blockIdx.x;
@@ -189,7 +208,8 @@ qk_norm_rope_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld_qkv, con
     sn[t] = sin_t[(long long)row * HALF + lane * E + t];
   }
 
-  for (int hh = warp; hh < nheads; hh += 4) {
+  // gridDim.y > 1 (few rows, e.g. a decode step): one head per warp, so the load -> reduce -> store chain runs once per warp
+  for (int hh = blockIdx.y * 4 + warp; hh < nheads; hh += 4 * gridDim.y) {
     const __nv_bfloat16* src = src_row + hh * D;
     float a[E], b[E];  // first-half / second-half elements owned by this lane
 #pragma unroll
@@ -580,7 +600,8 @@ extern "C" int bagel_rmsnorm_bf16(const void* x, long long ldx, const void* w0, 
   auto W0 = static_cast<const __nv_bfloat16*>(w0);
   auto W1 = static_cast<const __nv_bfloat16*>(w1);
   auto Y = static_cast<__nv_bfloat16*>(y);
-#define RMS_CASE(V) rmsnorm_kernel<V><<<grid, block, 0, s>>>(X, ldx, W0, W1, expert, Y, ldy, N, H, eps)
+  const bool pdl = pdl_small_enabled() && N <= 64;   // decode-sized calls only
+#define RMS_CASE(V) BAGEL_CUDA_CHECK(launch_maybe_pdl(rmsnorm_kernel<V>, grid, block, 0, s, pdl, X, ldx, W0, W1, expert, Y, ldy, N, H, eps))
   if (vpl <= 1) RMS_CASE(1);
   else if (vpl <= 2) RMS_CASE(2);
   else if (vpl <= 4) RMS_CASE(4);
@@ -642,8 +663,12 @@ extern "C" int bagel_qk_norm_rope(const void* qkv, long long ld_qkv, const void*
   static_cast<const __nv_bfloat16*>(qkv), ld_qkv, q_w0, k_w0, q_w1, k_w1, expert, cos_t, sin_t,                   \
       static_cast<__nv_bfloat16*>(q_out), ld_q, static_cast<__nv_bfloat16*>(k_out),                               \
       static_cast<__nv_bfloat16*>(v_out), ld_kv, kv_rows, N, Hq, Hk, eps, fp32_flow
-  if (D == 128) qk_norm_rope_kernel<128><<<N, 128, 0, s>>>(QK_ARGS);
-  else qk_norm_rope_kernel<64><<<N, 128, 0, s>>>(QK_ARGS);
+  // few rows (decode): spread the heads of a row over blockIdx.y — the per-head chain (load, warp reduce, store) is pure latency
+  static const bool spread = [] { const char* e = getenv("BAGEL_QKROPE_SPREAD"); return !(e && atoi(e) == 0); }();
+  const dim3 grid((unsigned)N, (spread && N <= 1024) ? (unsigned)((Hq + 2 * Hk + 3) / 4) : 1u);
+  const bool pdl = pdl_small_enabled() && N <= 64;
+  if (D == 128) BAGEL_CUDA_CHECK(launch_maybe_pdl(qk_norm_rope_kernel<128>, grid, dim3(128), 0, s, pdl, QK_ARGS));
+  else BAGEL_CUDA_CHECK(launch_maybe_pdl(qk_norm_rope_kernel<64>, grid, dim3(128), 0, s, pdl, QK_ARGS));
 #undef QK_ARGS
   COUNT_LAUNCH();
   BAGEL_CUDA_CHECK(cudaGetLastError());

@@ -30,6 +30,26 @@ int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t cols, u
 int make_tmap_4d_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
                            uint32_t box_w, uint32_t box_h, uint32_t stride);
 
+// Launch with (optionally) the programmatic-dependent-launch attribute: the kernel may become resident while its predecessor
+// in the stream is still running; it must execute griddepcontrol.wait (pdl_wait()) before touching the predecessor's data.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// BAGEL_PDL_SMALL=1: also launch the small glue kernels of a decode step (RMSNorm, q/k-norm + RoPE) with the PDL attribute
+bool pdl_small_enabled();
+
 #define BAGEL_CUDA_CHECK(expr)                                                                       \
   do {                                                                                               \
     cudaError_t _e = (expr);                                                                         \

@@ -4,7 +4,7 @@ ncu launch lists time each kernel alone, cold and serialised (short kernels are 
 CUDA events around single launches measure the host. This tool measures what a kernel costs INSIDE the replayed CUDA graph:
   (1) ablation: the 28-layer step graph with one kernel family removed (numerics are garbage, timing is not), and
   (2) a graph of 200 back-to-back launches of one small kernel (the floor a graph node costs).
-Usage: python tools/gpu_decode_ablate.py [layers=28] [B=32] [ctx=1245]"""
+Usage: python tools/gpu_decode_ablate.py [layers=28] [B=32] [ctx=1245] [quick]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -13,6 +13,7 @@ from bagel_b200 import ops, synthetic
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 ctx = int(sys.argv[3]) if len(sys.argv) > 3 else 1245
+quick = len(sys.argv) > 4 and sys.argv[4] == "quick"
 dev, BF16 = "cuda", torch.bfloat16
 model = synthetic.build_random_bagel(device=dev, seed=0, num_layers=layers)
 lm = model.language_model.model
@@ -94,11 +95,11 @@ def time_graph(fn, reps=15):
 
 full = time_graph(lambda: body())
 print(f"full step ({L} layers, B={B}, ctx={ctx}): {full:.3f} ms", flush=True)
-for name in ("norm", "qkv", "qkrope", "attn", "o", "gu", "down", "head"):
+for name in (("norm", "qkrope", "attn") if quick else ("norm", "qkv", "qkrope", "attn", "o", "gu", "down", "head")):
     t = time_graph(lambda: body((name,)))
     per = (full - t) * 1e3 / (L * (2 if name == "norm" else 1)) if name != "head" else (full - t) * 1e3
     print(f"  without {name:7s}: {t:.3f} ms  -> marginal {full - t:.3f} ms  ({per:.1f} us per launch)", flush=True)
-for combo in (("norm", "qkrope"), ("qkv", "o", "gu", "down", "head"), ("norm", "qkrope", "attn")):
+for combo in (() if quick else (("norm", "qkrope"), ("qkv", "o", "gu", "down", "head"), ("norm", "qkrope", "attn"))):
     t = time_graph(lambda: body(combo))
     print(f"  without {'+'.join(combo)}: {t:.3f} ms -> marginal {full - t:.3f} ms", flush=True)
 
