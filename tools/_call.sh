@@ -16,3 +16,8 @@ tail -n 30 gpurun_out/decode_ablate_*.txt
 # --- timeline of the two-tile attention kernel
 timeout 300 python tools/gpu_attn_trace.py run 4096 0 > gpurun_out/attn_trace_4096.txt 2>&1; echo rc=$?
 cat gpurun_out/attn_trace_4096.txt
+# --- VAE after the gn_finalize restructure
+timeout 600 python -m pytest tests/test_gpu_vae.py -x -q > gpurun_out/vae_tests.txt 2>&1; echo vae tests rc=$?
+tail -3 gpurun_out/vae_tests.txt
+timeout 600 python tools/gpu_perf_aux.py > gpurun_out/vae_siglip_timing.txt 2>&1; echo rc=$?
+tail -8 gpurun_out/vae_siglip_timing.txt
