@@ -8,11 +8,14 @@
 // back to back (it is the pacing stage, MUFU-bound at 1024 cycles per 128 x 128 block) and the tensor pipe follows one
 // block behind: P*V(g) as soon as P(g) arrives, then Q*K^T(g+2) into the buffer P(g) just left.
 //
-//   warps 0-3   softmax (thread = query row): tcgen05.ld S(g) -> exp2 (lazy rescaling, see attn.cu) -> P(g) as bf16 pairs
-//               into the first 64 columns of the same S buffer; the epilogue of item i is DEFERRED until block 0 of item
-//               i+1 has been handed to the tensor pipe (O is double buffered too), so waiting for the last P*V is hidden
-//   warp 4      scheduler + TMA producer: device work counter, Q tiles (double buffered), K_j / V_j ring
-//   warp 5      MMA issuer (one lane), software-pipelined over the stream of key blocks ACROSS work items
+//   warps 0-7   softmax, TWO threads per query row: warps 0-3 take keys 0-63 of a block, warps 4-7 keys 64-127 (warp w and
+//               w+4 sit on the same SM sub-partition and share its MUFU; one warp per sub-partition alone reaches only half
+//               of the MUFU rate — measured: 2090 cycles per block with 4 softmax warps). tcgen05.ld S(g) -> exp2 (lazy
+//               rescaling, see attn.cu; the two threads of a row agree on a redo through a 64-thread named barrier) ->
+//               P(g) as bf16 pairs over the first 32 columns of the thread's own 64 S columns; the epilogue of item i is
+//               DEFERRED until block 0 of item i+1 has been handed to the tensor pipe (O is double buffered too)
+//   warp 8      scheduler + TMA producer: device work counter, Q tiles (double buffered), K_j / V_j ring
+//   warp 9      MMA issuer (one lane), software-pipelined over the stream of key blocks ACROSS work items
 // TMEM (512 columns): S[0] [0,128)  S[1] [128,256)  O[0] [256,256+D)  O[1] [384,384+D).
 //
 // Same interface, masking rules and numerics as attn_varlen_kernel (attn.cu); reference seam: flash_attn_varlen_func at
@@ -34,7 +37,7 @@ namespace bagel {
 
 namespace {
 
-constexpr int kThreads3 = 6 * 32;   // 4 softmax warps + TMA warp + MMA warp
+constexpr int kThreads3 = 10 * 32;   // 8 softmax warps + TMA warp + MMA warp
 constexpr int kBM = 128;            // query rows per work item
 constexpr int kBN = 128;            // keys per block
 
@@ -56,7 +59,7 @@ template <int D>
 struct Cfg3 {
   static constexpr int kTileBytes = kBM * D * 2;
   static constexpr int kStages = (D == 128) ? 5 : 8;
-  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512;
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 320 + 1024 + 64;   // tiles, alignment, barriers, xch, flags
 };
 
 __device__ __forceinline__ float2 ffma2_(float2 a, float2 b, float2 c) {
@@ -127,7 +130,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   constexpr int kTileBytes = Cfg::kTileBytes;
   constexpr int kAtoms = D / 64;
   constexpr int kAtomBytes = kBM * 128;
-  constexpr int kSoftWarps = 4;
+  constexpr int kSoftWarps = 8;
   constexpr int kTmaWarp = kSoftWarps, kMmaWarp = kSoftWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
@@ -148,6 +151,8 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* sched_empty = sched_full + 2;   // [2]
   volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + 2);   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(sched_item) + 2);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);        // [2][128] row max / row sum exchange
+  volatile int* pair_flag = reinterpret_cast<volatile int*>(xch + 256);                 // [2 (block parity)][4 quarters][2 halves]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -300,7 +305,8 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < kBN / 16; ++k) {
             const uint64_t b_desc = umma_desc_mnmajor_sw128(vaddr + k * 2048, kAtomBytes);
-            umma_ts(tO, tS + k * 8, b_desc, idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+            // P: keys 0-63 over S columns [0,32) (softmax warps 0-3), keys 64-127 over S columns [64,96) (warps 4-7)
+            umma_ts(tO, tS + (k < 4 ? k * 8 : 64 + (k - 4) * 8), b_desc, idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
           }
         }
         umma_commit(&pv_done[g & 1]);
@@ -316,14 +322,17 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
   } else {
     // =========================== softmax / correction / epilogue ===========================
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = warp >> 2;             // 0: keys 0-63 of a block, 1: keys 64-127
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    constexpr int NC = kBN;
+    constexpr int NC = kBN / 2;             // score columns per thread
+    constexpr int DH = D / 2;               // O columns per thread (rescale / epilogue)
     uint32_t g = 0;      // global key-block counter (same sequence as the MMA lane's)
     uint32_t it = 0;     // item counter (items with key blocks)
     int slot = 0;
     uint32_t sphase = 0;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };   // warps w and w + 4
 
     // deferred epilogue of the previous item
     bool pend = false;
@@ -336,14 +345,14 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint32_t ob = pend_it & 1;
       mbar_wait(&o_full[ob], (pend_it >> 1) & 1);
       tc_fence_after();
-      const uint32_t tO = tmem_base + 256 + ob * 128 + lane_off;
+      const uint32_t tO = tmem_base + 256 + ob * 128 + half * DH + lane_off;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < DH / 32; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tO + c * 32, v);
         tmem_ld_wait();
         if (pend_row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(pend_row + c * 32);
+          uint4* dst = reinterpret_cast<uint4*>(pend_row + half * DH + c * 32);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint32_t o[4];
@@ -376,19 +385,21 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (nblk == 0) {   // rows that see no key at all (causal, Lq > Lk): zeros, as flash-attn does; no barrier involved
         if (qi < Lq) {
 #pragma unroll
-          for (int c = 0; c < D / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
+          for (int c = 0; c < DH / 8; ++c) reinterpret_cast<uint4*>(orow + half * DH)[c] = make_uint4(0u, 0u, 0u, 0u);
         }
         continue;
       }
 
+      // m: reference maximum of the row, identical in the two threads of a row by construction; l: this thread's share of
+      // the row sum (its 64 keys of every block)
       float m = -INFINITY, l = 0.f;
       constexpr float kRedoSum = 1073741824.0f;   // 2^30, see attn.cu
       for (int j = 0; j < nblk; ++j, ++g) {
-        const uint32_t tS = tmem_base + (g & 1) * 128 + lane_off;
+        const uint32_t tS = tmem_base + (g & 1) * 128 + half * NC + lane_off;   // this thread's 64 score columns; P goes to the first 32
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        const int kv0 = j * kBN;
-        const bool need_mask = (kv0 + kBN > Lk) || (p.causal && (kv0 + kBN - 1 > w.q0 + shift));
+        const int kv0 = j * kBN + half * NC;       // first key of this thread's columns
+        const bool need_mask = (kv0 + NC > Lk) || (p.causal && (kv0 + NC - 1 > w.q0 + shift));
         const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);
 
         uint32_t pk[NC / 2];
@@ -412,6 +423,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
         };
 
+        // m is the same in both threads of a row, so this vote has the same outcome in warp w and warp w + 4
         const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);
         bool redo = true;
         if (have_ref) {
@@ -419,27 +431,26 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           auto stream = [&](auto mask_tag) {
             uint32_t va[32], vb[32];
             tmem_ld_x32(tS + 0, va);
+            tmem_ld_x32(tS + 32, vb);
             tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < NC / 32; c += 2) {
-              if (c + 1 < NC / 32) tmem_ld_x32(tS + (c + 1) * 32, vb);
-              process_t(mask_tag, va, c, neg_ms);
-              if (c + 1 < NC / 32) {
-                tmem_ld_wait();
-                if (c + 2 < NC / 32) tmem_ld_x32(tS + (c + 2) * 32, va);
-                process_t(mask_tag, vb, c + 1, neg_ms);
-                if (c + 2 < NC / 32) tmem_ld_wait();
-              }
-            }
+            process_t(mask_tag, va, 0, neg_ms);
+            process_t(mask_tag, vb, 1, neg_ms);
           };
           if (need_mask) stream(std::true_type{});
           else stream(std::false_type{});
           const float rs_row = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
           redo = !(rs_row <= kRedoSum);
         }
+        // the two warps that share these rows must take the same path: exchange the warp votes
+        const bool warp_redo = __any_sync(0xffffffffu, redo);
+        volatile int* flags = pair_flag + (g & 1) * 8 + quarter * 2;
+        if (lane == 0) flags[half] = warp_redo ? 1 : 0;
+        pair_sync();
+        const bool pair_redo = (flags[0] | flags[1]) != 0;
         float alpha = 1.0f;
-        if (__any_sync(0xffffffffu, redo)) {
-          // slow path (first block of a row, or the running reference has become badly stale): exact two-pass on S
+        if (pair_redo) {
+          // slow path (first block of an item, or a reference that has become badly stale in either half): exact row maximum
+          // over all 128 keys, move m, recompute this thread's P, rescale its share of O and l
           float mx = -INFINITY;
 #pragma unroll 1
           for (int c = 0; c < NC / 32; ++c) {
@@ -453,34 +464,32 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               mx = fmaxf(mx, x);
             }
           }
-          float neg_ms = -m * p.scale_log2;
-          if (redo) {
-            const float m_new = fmaxf(m, mx);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            alpha = ex2_((m - m_use) * p.scale_log2);
-            m = m_new;
-            neg_ms = -m_use * p.scale_log2;
-            rs2[0] = make_float2(0.f, 0.f);
-            rs2[1] = make_float2(0.f, 0.f);
-          }
+          xch[half * 128 + row] = mx;
+          pair_sync();
+          mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
+          const float m_new = fmaxf(m, mx);
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha = ex2_((m - m_use) * p.scale_log2);   // m = -inf -> 0
+          m = m_new;
+          const float neg_ms = -m_use * p.scale_log2;
+          rs2[0] = make_float2(0.f, 0.f);
+          rs2[1] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < NC / 32; ++c) {
             uint32_t v[32];
             tmem_ld_x32(tS + c * 32, v);
             tmem_ld_wait();
-            if (redo) {
-              if (need_mask) process_t(std::true_type{}, v, c, neg_ms);
-              else process_t(std::false_type{}, v, c, neg_ms);
-            }
+            if (need_mask) process_t(std::true_type{}, v, c, neg_ms);
+            else process_t(std::false_type{}, v, c, neg_ms);
           }
           if (j > 0) {
             // O holds blocks 0..j-1 only once P*V(g-1) has COMPLETED; S(g) being ready does not imply that here (Q K^T of
             // block g is issued before P*V of block g-1), hence the explicit barrier
             mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();
-            const uint32_t tO = tmem_base + 256 + (it & 1) * 128 + lane_off;
+            const uint32_t tO = tmem_base + 256 + (it & 1) * 128 + half * DH + lane_off;
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
+            for (int c = 0; c < DH / 32; ++c) {
               uint32_t v[32];
               tmem_ld_x32(tO + c * 32, v);
               tmem_ld_wait();
@@ -492,9 +501,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
         const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
         l = l * alpha + rs;
-#pragma unroll
-        for (int c = 0; c < NC / 64; ++c)
-          tmem_st_x32(tS + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[c * 32]));
+        tmem_st_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -503,6 +510,13 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (j == 0 && pend) epilogue();   // the previous item's O: its last P*V has long finished by now
       }
 
+      // row sum = both halves, exchanged through shared memory. First barrier: the partner is past its read of the row
+      // maximum this thread may have left in the same slot during the last block's redo.
+      pair_sync();
+      xch[half * 128 + row] = l;
+      pair_sync();
+      l += xch[(half ^ 1) * 128 + row];
+      pair_sync();   // the partner has read this thread's value before the next item's first block overwrites it
       pend = true;
       pend_inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;
       pend_row_ok = qi < Lq;
