@@ -121,7 +121,10 @@ __device__ __forceinline__ Item3 decode_item3(int item, const Attn3Params& p) {
   return w;
 }
 
-template <int D>
+// QT: the Q tile is copied from shared memory into TMEM once per item (tcgen05.cp) and Q K^T runs with its A operand in
+// TMEM: an SS-mode 128x128x16 MMA reads 8 KB of shared memory (the SM's whole 128 B/clk), with Q in TMEM only K is read.
+// TMEM then holds ONE O buffer: S[0] S[1] O Q[0] Q[1] = 128 + 128 + 128 + 64 + 64 columns.
+template <int D, bool QT>
 __global__ void __launch_bounds__(kThreads3, 1)
 attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
@@ -248,14 +251,35 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         mbar_wait(&kv_full[st], use & 1);
         return smem_u32(smem_kv + st * kTileBytes);
       };
+      // QT: first block of an item -> copy its Q tile smem -> TMEM (8 columns = 16 d per 128x256b copy); the copies and the
+      // MMAs of this thread execute in issue order, so no barrier is needed in between, and the smem buffer is free afterwards
+      auto stage_q = [&](uint32_t qb) {
+        if constexpr (QT) {
+          const uint32_t tQ = tmem_base + 384 + qb * 64;
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a) {
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + qb * kTileBytes + a * kAtomBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tQ + (a * 4 + k) * 8), "l"(a_desc + 2 * k) : "memory");
+          }
+          umma_commit(&q_empty[qb]);
+        }
+      };
       auto issue_qk = [&](uint32_t g, uint32_t qb, uint32_t kaddr) {
         const uint32_t tS = tmem_base + (g & 1) * 128;
 #pragma unroll
         for (int a = 0; a < kAtoms; ++a) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + qb * kTileBytes + a * kAtomBytes));
           const uint64_t b_desc = umma_desc_kmajor_sw128(kaddr + a * kAtomBytes);
+          if constexpr (QT) {
+            const uint32_t tQ = tmem_base + 384 + qb * 64;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, (a | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_ts(tS, tQ + (a * 4 + k) * 8, b_desc + 2 * k, idesc_qk, (a | k) != 0);
+          } else {
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + qb * kTileBytes + a * kAtomBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(tS, a_desc + 2 * k, b_desc + 2 * k, idesc_qk, (a | k) != 0);
+          }
         }
         umma_commit(&s_full[g & 1]);
         umma_commit(&kv_empty[(2 * g) % kStages]);
@@ -270,8 +294,9 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         mbar_wait(&q_full[0], 0);
         const uint32_t kaddr = kv_wait(0);
         tc_fence_after();
+        stage_q(0);
         issue_qk(0, 0, kaddr);
-        if (cur.nblk == 1) umma_commit(&q_empty[0]);
+        if (!QT && cur.nblk == 1) umma_commit(&q_empty[0]);
       }
       while (have) {
         // ---- look one block ahead: Q K^T of block g+1 goes out before P*V of block g ----
@@ -289,14 +314,17 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           if (nj == 0) mbar_wait(&q_full[qb], (nit >> 1) & 1);
           const uint32_t kaddr = kv_wait(2 * (g + 1));
           tc_fence_after();
+          // QT: TMEM Q buffer qb was last read by the Q K^T MMAs of item nit-2, all issued before this point (in-order pipe)
+          if (nj == 0) stage_q(qb);
           // S buffer (g+1)&1 held P(g-1): P*V(g-1) was issued in the previous round and the pipe executes in issue order
           issue_qk(g + 1, qb, kaddr);
-          if (nj == nxt.nblk - 1) umma_commit(&q_empty[qb]);   // that was the item's last QK^T
+          if (!QT && nj == nxt.nblk - 1) umma_commit(&q_empty[qb]);   // that was the item's last QK^T
         }
         // ---- P*V of block g ----
         const uint32_t vaddr = kv_wait(2 * g + 1);
-        const uint32_t ob = it & 1;
-        if (j == 0 && it >= 2) mbar_wait(&o_free[ob], ((it >> 1) - 1) & 1);   // item it-2's O has been read out
+        const uint32_t ob = QT ? 0u : (it & 1);                 // O buffer; its use number:
+        const uint32_t ou = QT ? it : (it >> 1);
+        if (j == 0 && ou >= 1) mbar_wait(&o_free[ob], (ou - 1) & 1);   // the previous user's O has been read out
         mbar_wait(&p_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
         {
@@ -342,8 +370,8 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     uint32_t pend_it = 0;
 
     auto epilogue = [&]() {
-      const uint32_t ob = pend_it & 1;
-      mbar_wait(&o_full[ob], (pend_it >> 1) & 1);
+      const uint32_t ob = QT ? 0u : (pend_it & 1);
+      mbar_wait(&o_full[ob], (QT ? pend_it : (pend_it >> 1)) & 1);
       tc_fence_after();
       const uint32_t tO = tmem_base + 256 + ob * 128 + half * DH + lane_off;
 #pragma unroll
@@ -487,7 +515,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             // block g is issued before P*V of block g-1), hence the explicit barrier
             mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after();
-            const uint32_t tO = tmem_base + 256 + (it & 1) * 128 + half * DH + lane_off;
+            const uint32_t tO = tmem_base + 256 + (QT ? 0u : (it & 1)) * 128 + half * DH + lane_off;
 #pragma unroll
             for (int c = 0; c < DH / 32; ++c) {
               uint32_t v[32];
@@ -552,11 +580,11 @@ int* sched_counter3(cudaStream_t stream) {
   return c;
 }
 
-template <int D>
+template <int D, bool QT>
 int launch3(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, Attn3Params p, int B, int max_seqlen_q,
             cudaStream_t stream) {
   using Cfg = Cfg3<D>;
-  auto kern = attn3_kernel<D>;
+  auto kern = attn3_kernel<D, QT>;
   static bool attr_done = false;
   if (!attr_done) {
     BAGEL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -595,8 +623,12 @@ int attn3_varlen(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorM
   p.Hk = Hk;
   p.causal = causal;
   p.scale_log2 = scale_log2;
-  if (head_dim == 128) return launch3<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream);
-  return launch3<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream);
+  static const bool qt = [] { const char* e = getenv("BAGEL_ATTN_QT"); return e && atoi(e) != 0; }();
+  if (head_dim == 128)
+    return qt ? launch3<128, true>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream)
+              : launch3<128, false>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream);
+  return qt ? launch3<64, true>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream)
+            : launch3<64, false>(tmQ, tmK, tmV, p, batch, max_seqlen_q, stream);
 }
 
 }  // namespace bagel

@@ -180,6 +180,20 @@ def test_attn_varlen(lq, lk, Hq, Hk, D, causal):
     torch.testing.assert_close(out.float().cpu(), ref, atol=2e-2, rtol=2e-2)
 
 
+def test_attn_varlen_v3_experimental_kernel():
+    """The double-buffered-S kernel (csrc/attn3.cu, off by default: BAGEL_ATTN_V3 is read once per process) must stay correct:
+    the packed-attention cases above and the adversarial lazy-rescale cases, in a child process with the kernel switched on."""
+    import os, subprocess, sys
+    if os.environ.get("BAGEL_ATTN_V3"):
+        pytest.skip("already running with BAGEL_ATTN_V3")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BAGEL_ATTN_V3="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", "tests/test_gpu_kernels.py",
+                        "tests/test_gpu_attn_adversarial.py", "-k", "test_attn_varlen or adversarial or lazy or attn_"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 DECODE_CASES = [  # (lens_k, Hq, Hk, spare rows per sample, q present per sample)
     ([1245] * 8, 28, 4, 16, None), ([17, 300, 1, 5000], 28, 4, 0, None), ([33, 64, 127], 8, 8, 3, None),
     ([700, 2, 129, 4097], 16, 4, 5, None), ([256, 31], 4, 2, 0, None), ([90, 0, 513], 8, 1, 2, None),

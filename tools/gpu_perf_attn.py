@@ -2,7 +2,10 @@
 import sys, torch
 sys.path.insert(0, ".")
 from bagel_b200 import ops
+import os
 try:
+    if os.environ.get("PERF_NO_FA2"):
+        raise ImportError("PERF_NO_FA2 set")
     from flash_attn import flash_attn_varlen_func
 except Exception as e:
     flash_attn_varlen_func = None
