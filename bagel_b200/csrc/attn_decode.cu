@@ -248,18 +248,28 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   // ---- merge: CTAs of the cluster -> rank 0 (distributed shared memory), fixed rank order ----
   if (p.split > 1) cluster_sync_all(); else __syncthreads();
   if (rank == 0 && active) {
+    // All distributed-shared-memory reads of a head are issued together (fixed trip count + predicate: with a run-time loop
+    // bound every read waited for the previous one, ~300 cycles each, 8 per head on the critical path of every cluster).
+    constexpr int kMaxSplit = 8;
 #pragma unroll
     for (int h = 0; h < G; ++h) {
+      float mr[kMaxSplit], lr[kMaxSplit], ar[kMaxSplit];
+#pragma unroll
+      for (int r = 0; r < kMaxSplit; ++r) {
+        const bool on = r < p.split;
+        mr[r] = !on ? -INFINITY : (p.split > 1 ? ld_dsmem_f32(&part_m[h], r) : part_m[h]);
+        lr[r] = !on ? 0.f : (p.split > 1 ? ld_dsmem_f32(&part_l[h], r) : part_l[h]);
+        ar[r] = !on ? 0.f : (p.split > 1 ? ld_dsmem_f32(&part_acc[h][t], r) : part_acc[h][t]);
+      }
       float M = -INFINITY;
-      for (int r = 0; r < p.split; ++r) M = fmaxf(M, p.split > 1 ? ld_dsmem_f32(&part_m[h], r) : part_m[h]);
+#pragma unroll
+      for (int r = 0; r < kMaxSplit; ++r) M = fmaxf(M, mr[r]);
       float L = 0.f, A = 0.f;
-      for (int r = 0; r < p.split; ++r) {
-        const float mr = p.split > 1 ? ld_dsmem_f32(&part_m[h], r) : part_m[h];
-        const float lr = p.split > 1 ? ld_dsmem_f32(&part_l[h], r) : part_l[h];
-        const float ar = p.split > 1 ? ld_dsmem_f32(&part_acc[h][t], r) : part_acc[h][t];
-        const float wt = (mr == -INFINITY) ? 0.f : ex2f(mr - M);
-        L = fmaf(lr, wt, L);
-        A = fmaf(ar, wt, A);
+#pragma unroll
+      for (int r = 0; r < kMaxSplit; ++r) {   // fixed rank order: deterministic
+        const float wt = (mr[r] == -INFINITY) ? 0.f : ex2f(mr[r] - M);
+        L = fmaf(lr[r], wt, L);
+        A = fmaf(ar[r], wt, A);
       }
       const float ov = (L > 0.f) ? A / L : 0.f;
       p.out[(long long)q_row * p.ld_out + (hk * G + h) * kD + t] = __float2bfloat16_rn(ov);
