@@ -293,10 +293,11 @@ def test_qk_norm_rope_matches_oracle(D, Hq, Hk, flow):
         return torch.where(exc[:, None, None], om.rms_norm(t, wg.cpu(), 1e-6), om.rms_norm(t, wu.cpu(), 1e-6))
 
     qr, kr = om.apply_rope(nrm(q, qw[0], qw[1]), nrm(k, kw[0], kw[1]), c_ref, s_ref)
-    # outputs are sums of two O(1) products: a 1-ulp difference in an operand (rsqrt / cos ulp) shows up as an
-    # absolute error of ~2^-8 even when the sum itself is small
-    _assert_bf16_close(q_out.cpu().reshape(N, Hq, D), qr.to(torch.bfloat16), ulps=1.01, atol=4e-3)
-    _assert_bf16_close(kbuf[rows.long()].cpu().reshape(N, Hk, D), kr.to(torch.bfloat16), ulps=1.01, atol=4e-3)
+    # outputs are sums of two O(1) products: a 1-ulp difference in an operand (rsqrt / cos ulp, which also depends on the
+    # HOST cpu's vector math the oracle runs on) shows up as an absolute error of ~2^-7 even when the sum itself is small
+    # (seen once on a different box: 2 bf16 ulps at |x| = 1.35 with atol 4e-3)
+    _assert_bf16_close(q_out.cpu().reshape(N, Hq, D), qr.to(torch.bfloat16), ulps=1.01, atol=8e-3)
+    _assert_bf16_close(kbuf[rows.long()].cpu().reshape(N, Hk, D), kr.to(torch.bfloat16), ulps=1.01, atol=8e-3)
     assert (q_out.cpu().reshape(N, Hq, D) != qr.to(torch.bfloat16)).float().mean().item() < 5e-3
     assert torch.equal(vbuf[rows.long()].cpu().reshape(N, Hk, D), v)
 
