@@ -95,6 +95,46 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// tcgen05.mma with the operand descriptors given by their LOW words only. All operand tiles of this kernel share the high
+// word (SBO = 1024 B, descriptor version 1, SWIZZLE_128B), and between the MMAs of one key block only the 14-bit start
+// address field (address >> 4) in the low word moves. The single issuing lane's instruction stream paces the whole loop
+// (ncu source view: ~80 cycles of ALU + ELECT + R2UR.BROADCAST + BRA.U.ANY per MMA against 58-64 cycles of tensor work), so
+// every 64-bit add-with-carry and every R2UR of a constant removed from it shortens the key-block period.
+constexpr uint32_t kDescHiSw128 = 0x40004040u;   // bits 32..63 of umma_desc_{kmajor,mnmajor}_sw128()
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return (smem_addr & 0x3FFFF) >> 4; }
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 hi;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b32 hi, %5;\n\t"
+      "mov.b64 da, {%1, hi};\n\t"
+      "mov.b64 db, {%2, hi};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 hi;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b32 hi, %5;\n\t"
+      "mov.b64 db, {%2, hi};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(kDescHiSw128)
+      : "memory");
+}
+
 // One unit of work: two 128-row query tiles of one (sample, head) against that sample's keys.
 struct AttnItem {
   int b, h, hk;
@@ -205,7 +245,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == kTmaWarp) {
     // =========================== scheduler + TMA producer ===========================
-    if (lane == 0) {
+    if (elect_one_lane()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t q_phase = 0;
@@ -245,7 +285,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (elect_one_lane()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S[128,128] = Q[128,D] K[128,D]^T
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, D, 0, 1);        // O[128,D] += P[128,128] V[128,D]
       int stage = 0;
@@ -257,26 +297,28 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t sphase = 0;
       [[maybe_unused]] int tr_it = 0;
 
+      const uint32_t q_lo[2] = {desc_lo_kmajor(smem_u32(smem_q)), desc_lo_kmajor(smem_u32(smem_q + kTileBytes))};
       auto issue_qk = [&](int t, int kstage) {
-        // K-major operands: D columns = kAtoms atoms of 64; 4 UMMA_K=16 steps per atom (+32 B each)
+        // K-major operands: D columns = kAtoms atoms of 64 (+1024 in the address field per 16 KB atom); 4 UMMA_K=16 steps per
+        // atom (+2 = 32 B each)
+        const uint32_t k_lo = desc_lo_kmajor(smem_u32(smem_kv + kstage * kTileBytes));
 #pragma unroll
         for (int a = 0; a < kAtoms; ++a) {
-          const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem_q + t * kTileBytes + a * kAtomBytes));
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(smem_kv + kstage * kTileBytes + a * kAtomBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_S[t], a_desc + 2 * k, b_desc + 2 * k, idesc_qk, (a | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t off = (uint32_t)(a * (kAtomBytes >> 4) + 2 * k);
+            umma_ss_lo(tmem_S[t], q_lo[t] + off, k_lo + off, idesc_qk, (a | k) != 0);
+          }
         }
         umma_commit(&s_bar[t]);
       };
       auto issue_pv = [&](int t, int vstage, bool accumulate) {
         // A = P_t from TMEM (bf16 pairs: 16 keys = 8 columns per UMMA_K step);
-        // B = V block, MN-major: 64-col halves LBO = kAtomBytes apart, 8-key groups 1024 B apart, 16 keys = 2048 B
-        const uint32_t vbase = smem_u32(smem_kv + vstage * kTileBytes);
+        // B = V block, MN-major: 64-col halves LBO = kAtomBytes apart, 8-key groups 1024 B apart, 16 keys = 2048 B (+128)
+        const uint32_t v_lo = desc_lo_mnmajor(smem_u32(smem_kv + vstage * kTileBytes), kAtomBytes);
 #pragma unroll
-        for (int k = 0; k < kBlockN / 16; ++k) {
-          const uint64_t b_desc = umma_desc_mnmajor_sw128(vbase + k * 2048, kAtomBytes);
-          umma_ts(tmem_O[t], tmem_S[t] + k * 8, b_desc, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < kBlockN / 16; ++k)
+          umma_ts_lo(tmem_O[t], tmem_S[t] + k * 8, v_lo + (uint32_t)(k * (2048 >> 4)), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
       };
 
       while (true) {

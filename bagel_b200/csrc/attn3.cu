@@ -189,7 +189,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
   if (warp == kTmaWarp) {
     // =========================== scheduler + TMA producer ===========================
-    if (lane == 0) {
+    if (elect_one_lane()) {
       uint32_t n_load = 0;     // K/V tiles loaded so far (slot = n % kStages, use number = n / kStages)
       uint32_t it = 0;         // items with key blocks so far (Q buffer = it & 1)
       int slot = 0;
@@ -228,7 +228,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (elect_one_lane()) {   // see common.cuh: `lane == 0` would cost ~80 cycles of wrapper code per MMA
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBM, kBN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBM, D, 0, 1);
       int slot = 0;

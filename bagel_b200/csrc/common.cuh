@@ -71,6 +71,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Exactly one lane of a CONVERGED warp. Use this — not `lane == 0` — to guard single-thread tcgen05 / TMA issue: with
+// elect.sync ptxas knows one thread runs the region and keeps descriptors on the uniform datapath (UIADD3 + back-to-back
+// UTCHMMA). Behind `lane == 0` it wraps EVERY tcgen05.mma in ELECT / 4-5 x R2UR.BROADCAST / PLOP3 / BRA.U.ANY, ~80 cycles of
+// dependent instruction stream per MMA (measured in the attention kernel, whose 64-cycle MMAs it paced).
+__device__ __forceinline__ bool elect_one_lane() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor is still running; it must execute pdl_wait() before touching anything the predecessor
 // produces (or writing anything it reads). pdl_launch_dependents() lets the NEXT such kernel start early.

@@ -78,7 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_lane()) {   // not `lane == 0`: see common.cuh
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : ((p.hints & 8) ? kEvictLast : kEvictNormal);
@@ -109,7 +109,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_lane()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;

@@ -90,7 +90,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one_lane()) {   // not `lane == 0`: see common.cuh
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t hint_a = (p.hints & 2) ? kEvictFirst : ((p.hints & 8) ? kEvictLast : kEvictNormal);
@@ -111,7 +111,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader && elect_one_lane()) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);  // M = 256 across the pair
       int stage = 0;
       uint32_t phase = 0;

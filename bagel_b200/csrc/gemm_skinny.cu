@@ -115,7 +115,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   pdl_launch_dependents();   // the next PDL kernel may start its own weight prefetch while this one streams
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_lane()) {   // not `lane == 0`: see common.cuh
       // The weights do not depend on the kernel in front of this one: fill the (empty) ring with W tiles right away,
       // resolve the grid dependency, then add the token tiles of the same stages (same mbarrier, one expect_tx).
       const int npre = min(p.stages, kb_end - kb_begin);
@@ -139,7 +139,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_lane()) {   // not `lane == 0`: see common.cuh
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.MT, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
