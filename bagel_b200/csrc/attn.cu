@@ -63,12 +63,16 @@ struct AttnParams {
   int qtiles;        // work items per (sample, head): ceil(max_seqlen_q / 256)
   int num_items;     // qtiles * Hq * batch
   int* sched;        // device counter (zeroed before the launch): next work item to hand out
+  int poly;          // every 4th score pair of interior key blocks takes the FMA-pipe exp2 (BAGEL_ATTN_POLY)
 };
 
 template <int D>
 struct AttnCfg {
   static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
-  static constexpr int kStages = (D == 128) ? 4 : 6;
+#ifndef BAGEL_ATTN_STAGES128
+#define BAGEL_ATTN_STAGES128 5
+#endif
+  static constexpr int kStages = (D == 128) ? BAGEL_ATTN_STAGES128 : 6;
   static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512;
 };
 
@@ -93,6 +97,31 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA pipe for a PAIR of scores (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic add,
+// degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 1.0e-4, 40x below the bf16 rounding of P), and n added
+// to the exponent field with one integer multiply-add. Valid for x <= ~100; x below -126 (masked-out -inf included) clamps to
+// 2^-126, NOT to 0 — so it is only used in interior key blocks, never where a mask could leave a row without any visible key.
+// With one softmax warp of each tile per SM sub-partition the exp2 stream is MUFU-bound (16 exp2 / clk / SM = 2048 clk per
+// pair of 128 x 128 blocks, as long as the two tensor-core GEMMs of those blocks); every 4th score pair goes through this path.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), neg_magic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 neg1 = make_float2(-1.0f, -1.0f), one = make_float2(1.0f, 1.0f);
+  const float2 c1 = make_float2(0.69328292f, 0.69328292f), c2 = make_float2(0.24221068f, 0.24221068f),
+               c3 = make_float2(0.05500873f, 0.05500873f);
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = fadd2(x, magic);            // integer part in the low mantissa bits
+  const float2 n = fadd2(t, neg_magic);        // exact
+  const float2 f = ffma2(n, neg1, x);          // x - n, in [-0.5, 0.5]
+  float2 q = ffma2(f, c3, c2);
+  q = ffma2(q, f, c1);
+  q = ffma2(q, f, one);
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
 }
 
 // tcgen05.mma with the operand descriptors given by their LOW words only. All operand tiles of this kernel share the high
@@ -441,8 +470,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         // kMask is a compile-time tag: interior blocks (the vast majority) must not carry the predicated-off compare /
         // select instructions of the masked variant — they still cost issue slots (310 of 700 per block and thread)
-        auto process_t = [&](auto mask_tag, const uint32_t (&v)[32], int c, float neg_ms) {
+        auto process_t = [&](auto mask_tag, auto poly_tag, const uint32_t (&v)[32], int c, float neg_ms) {
           constexpr bool kMask = decltype(mask_tag)::value;
+          constexpr bool kPoly = decltype(poly_tag)::value && !kMask;
           const float2 nm2 = make_float2(neg_ms, neg_ms);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -452,7 +482,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               if (kv0 + c * 32 + 2 * i + 1 > lim) x1 = -INFINITY;
             }
             const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
-            const float2 e = make_float2(ex2(x.x), ex2(x.y));
+            const float2 e = (kPoly && (i & 3) == 3) ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
             rs2[i & 1] = fadd2(rs2[i & 1], e);
             pk[c * 16 + i] = pack_bf16x2(e.x, e.y);
           }
@@ -463,24 +493,25 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         bool redo = true;
         if (have_ref) {
           const float neg_ms = -m * p.scale_log2;
-          auto stream = [&](auto mask_tag) {
+          auto stream = [&](auto mask_tag, auto poly_tag) {
             uint32_t va[32], vb[32];
             tmem_ld_x32(tS + 0, va);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < NC / 32; c += 2) {
               if (c + 1 < NC / 32) tmem_ld_x32(tS + (c + 1) * 32, vb);
-              process_t(mask_tag, va, c, neg_ms);
+              process_t(mask_tag, poly_tag, va, c, neg_ms);
               if (c + 1 < NC / 32) {
                 tmem_ld_wait();
                 if (c + 2 < NC / 32) tmem_ld_x32(tS + (c + 2) * 32, va);
-                process_t(mask_tag, vb, c + 1, neg_ms);
+                process_t(mask_tag, poly_tag, vb, c + 1, neg_ms);
                 if (c + 2 < NC / 32) tmem_ld_wait();
               }
             }
           };
-          if (need_mask) stream(std::true_type{});
-          else stream(std::false_type{});
+          if (need_mask) stream(std::true_type{}, std::false_type{});
+          else if (p.poly) stream(std::false_type{}, std::true_type{});
+          else stream(std::false_type{}, std::false_type{});
           const float rs_row = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
           redo = !(rs_row <= kRedoSum);
           if (tr_on) ATTN_TRACE(t, tr_it, 2);
@@ -518,8 +549,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld_x32(tS + c * 32, v);
             tmem_ld_wait();
             if (redo) {
-              if (need_mask) process_t(std::true_type{}, v, c, neg_ms);
-              else process_t(std::false_type{}, v, c, neg_ms);
+              if (need_mask) process_t(std::true_type{}, std::false_type{}, v, c, neg_ms);
+              else process_t(std::false_type{}, std::false_type{}, v, c, neg_ms);
             }
           }
           if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
@@ -692,6 +723,8 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.Hk = num_heads_k;
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return (e && atoi(e) != 0) ? 1 : 0; }();
+  p.poly = poly;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (head_dim == 128) return launch_attn<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
   return launch_attn<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);

@@ -1,8 +1,12 @@
 """Attention microbench (BASELINE configs[4]): packed varlen, d=128, bf16; ours vs flash_attn 2.8 (FA2 SASS on sm_100)."""
 import sys, torch
 sys.path.insert(0, ".")
-from bagel_b200 import ops
 import os
+if os.environ.get("PERF_LIB"):      # same-box A/B against a variant build (tools/build_variant.py)
+    from pathlib import Path
+    from bagel_b200 import _cabi
+    _cabi.LIB_PATH = Path(os.environ["PERF_LIB"]).resolve()
+from bagel_b200 import ops
 try:
     if os.environ.get("PERF_NO_FA2"):
         raise ImportError("PERF_NO_FA2 set")
