@@ -69,8 +69,9 @@ struct AttnParams {
 template <int D>
 struct AttnCfg {
   static constexpr int kTileBytes = kBlockM * D * 2;  // one Q tile / one K block / one V block
+// 4 stages measured equal or better than 5 on one box (profiles/r02_attn_poly_stages_ab.txt); -D for A/B builds
 #ifndef BAGEL_ATTN_STAGES128
-#define BAGEL_ATTN_STAGES128 5
+#define BAGEL_ATTN_STAGES128 4
 #endif
   static constexpr int kStages = (D == 128) ? BAGEL_ATTN_STAGES128 : 6;
   static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512;
@@ -723,8 +724,10 @@ extern "C" int bagel_attn_varlen_fwd(const void* q, const void* k, const void* v
   p.Hk = num_heads_k;
   p.causal = causal;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  static const int poly = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return (e && atoi(e) != 0) ? 1 : 0; }();
-  p.poly = poly;
+  // FMA-pipe exp2 for every 4th score pair: +2-6 % on long non-causal sweeps (denoise, ViT), neutral to -9 % on short causal
+  // ones (profiles/r02_attn_poly_stages_ab.txt) -> on for non-causal calls; BAGEL_ATTN_POLY=0/1 forces it off / on
+  static const int poly_env = [] { const char* e = getenv("BAGEL_ATTN_POLY"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  p.poly = poly_env >= 0 ? poly_env : (causal ? 0 : 1);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (head_dim == 128) return launch_attn<128>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
   return launch_attn<64>(tmQ, tmK, tmV, p, batch, max_seqlen_q, s);
