@@ -375,6 +375,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         for (int j = 0; j < nblk; ++j) {
           const int vstage = stage;
+          ATTN_TRACE(2, tr_it, 4);
           mbar_wait(&kv_full[vstage], phase);  // V_j
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           const int kstage = stage;
@@ -384,6 +385,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           tc_fence_after();
+          ATTN_TRACE(2, tr_it, 5);
           for (int t = 0; t < ntile; ++t) {
             if (j >= w.nblk_t[t]) continue;      // causal: this block lies entirely above the tile's diagonal
             const bool t_next = (j + 1) < w.nblk_t[t];
@@ -406,6 +408,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_commit(&kv_empty[vstage]);
           if (has_next) umma_commit(&kv_empty[kstage]);
           if (has_next && j + 2 == nblk) umma_commit(q_empty);   // that was the item's last QK^T
+          ATTN_TRACE(2, tr_it - 1, 6);
         }
         for (int t = 0; t < ntile; ++t)
           if (w.nblk_t[t] > 0) ++icnt[t];

@@ -67,6 +67,11 @@ def run(L=4096, causal=0, B=4, Hq=28, Hk=4, D=128):
         mm = m[m[:, 3] == tile]
         print(f"MMA lane, tile {tile}: wait for P {np.median(mm[:,1]-mm[:,0]):.0f} clk | issue PV+QK {np.median(mm[:,2]-mm[:,1]):.0f} | "
               f"period {np.median(np.diff(mm[:,1])):.0f}")
+    m0_, m1_ = m[m[:, 3] == 0], m[m[:, 3] == 1]
+    k = min(len(m0_), len(m1_)) - 1
+    if k > 10:
+        print(f"MMA lane per key block: wait for V_j + K_j+1 {np.median(m0_[:k,5]-m0_[:k,4]):.0f} clk | commits after the 2nd tile's issue "
+              f"{np.median(m1_[:k,6]-m1_[:k,2]):.0f} | loop turn-around {np.median(m0_[1:k+1,4]-m1_[:k,6]):.0f}")
     # latency from the softmax arrive to the MMA lane seeing it, and from MMA issue to the softmax seeing S
     s0 = t[0, lo:hi]
     m0 = m[m[:, 3] == 0]
