@@ -55,13 +55,15 @@ def run(L=4096, causal=0, B=4, Hq=28, Hk=4, D=128):
     lib.bagel_attn_trace_read.argtypes = [P, ctypes.c_int]
     assert lib.bagel_attn_trace_read(buf, n) == 0
     t = np.frombuffer(buf, dtype=np.int64).reshape(3, 1024, 8)
-    lo, hi = 40, 1000     # steady-state iterations
+    lo = 40               # steady-state iterations: skip the ramp, stop where CTA 0 ran out of work (unwritten entries are 0)
     for tile in (0, 1):
+        hi = max(lo + 2, int((t[tile, :, 1] > 0).sum()) - 4)
         e = t[tile, lo:hi]
         per = np.diff(e[:, 1])
         print(f"softmax tile {tile}: period {np.median(per):.0f} clk | wait for S {np.median(e[:,1]-e[:,0]):.0f} | "
               f"S ready -> exps issued {np.median(e[:,2]-e[:,1]):.0f} | -> P stored {np.median(e[:,3]-e[:,2]):.0f} | "
               f"-> arrive {np.median(e[:,4]-e[:,3]):.0f} | arrive -> next wait {np.median(e[1:,0]-e[:-1,4]):.0f}")
+    hi = max(lo + 2, int((t[2, :, 1] > 0).sum()) // 2 - 4)
     m = t[2, 2 * lo:2 * hi]
     for tile in (0, 1):
         mm = m[m[:, 3] == tile]
@@ -73,7 +75,7 @@ def run(L=4096, causal=0, B=4, Hq=28, Hk=4, D=128):
         print(f"MMA lane per key block: wait for V_j + K_j+1 {np.median(m0_[:k,5]-m0_[:k,4]):.0f} clk | commits after the 2nd tile's issue "
               f"{np.median(m1_[:k,6]-m1_[:k,2]):.0f} | loop turn-around {np.median(m0_[1:k+1,4]-m1_[:k,6]):.0f}")
     # latency from the softmax arrive to the MMA lane seeing it, and from MMA issue to the softmax seeing S
-    s0 = t[0, lo:hi]
+    s0 = t[0, lo:max(lo + 2, int((t[0, :, 1] > 0).sum()) - 4)]
     m0 = m[m[:, 3] == 0]
     # align by nearest following stamp
     arr = s0[:, 4]
