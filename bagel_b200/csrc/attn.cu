@@ -733,6 +733,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
           };
+          // (A chunk-level classification of boundary blocks — skip the chunks no row of the warp can see, unmasked code for the
+          // chunks every row sees in full — was measured SLOWER than masking the whole block per element: it gives up the
+          // double-buffered loads and bloats the loop; profiles/r02_attn_halfrow_ab.txt, last section.)
           if (need_mask) stream(std::true_type{}, std::false_type{});
           else if (p.poly) stream(std::false_type{}, std::true_type{});
           else stream(std::false_type{}, std::false_type{});
