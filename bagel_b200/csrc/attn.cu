@@ -47,17 +47,7 @@ __device__ long long g_attn_trace[3 * kTraceIters * kTraceEvents];
 #define ATTN_TRACE(role, iter, ev) do { } while (0)
 #endif
 
-// BAGEL_ATTN_HALFROW (build-time, default 0; tools/build_variant.py for same-box A/Bs): TWO softmax threads per query row —
-// 8 softmax warps per tile, the second group taking keys 64-127 of every block. A warp's tcgen05.ld does not overlap its own
-// math (profiles/r02_microbench_tmem_mufu.txt: 847 clk of math + 571 clk of loads = 1416 clk per block), two warps on one SM
-// sub-partition overlap each other's (1156 clk per block). Costs 576 threads = 112 registers per thread.
-#ifndef BAGEL_ATTN_HALFROW
-#define BAGEL_ATTN_HALFROW 0
-#endif
-constexpr int kSoftGroups = BAGEL_ATTN_HALFROW ? 2 : 1;          // softmax warp groups (of 4 warps) per tile
-// HALFROW == 2: two idle warps complete the fifth warpgroup so that setmaxnreg can move registers from it to the softmax warps
-// (HALFROW == 1: 576 threads at 96 registers, no setmaxnreg)
-constexpr int kAttnThreads = (8 * kSoftGroups + (BAGEL_ATTN_HALFROW == 2 ? 4 : 2)) * 32;   // softmax warps of both tiles + TMA warp + MMA warp
+constexpr int kAttnThreads = (8 + 2) * 32;  // softmax warps of both tiles (4 + 4) + TMA warp + MMA warp
 constexpr int kBlockM = 128;  // rows per query tile (2 tiles per work item)
 constexpr int kBlockN = 128;  // keys per block
 
@@ -84,7 +74,7 @@ struct AttnCfg {
 #define BAGEL_ATTN_STAGES128 4
 #endif
   static constexpr int kStages = (D == 128) ? BAGEL_ATTN_STAGES128 : 6;
-  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512 + (BAGEL_ATTN_HALFROW ? 2048 + 128 : 0);
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 1024 + 512;
 };
 
 // packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of FMA / ADD
@@ -231,7 +221,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int kTileBytes = Cfg::kTileBytes;
   constexpr int kAtoms = D / 64;               // 64-column (128 B) swizzle atoms per row
   constexpr int kAtomBytes = kBlockM * 128;    // one [128 rows x 64 cols] box
-  constexpr int kSoftWarps = 4 * kSoftGroups;  // softmax warps per tile
+  constexpr int kSoftWarps = 4;                // softmax warps per tile
   constexpr int kTmaWarp = 2 * kSoftWarps, kMmaWarp = 2 * kSoftWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
@@ -280,21 +270,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-#if BAGEL_ATTN_HALFROW == 2
-  // 640 threads start with 96 registers each; the pool setmaxnreg draws on is what the CTA itself releases: the TMA / MMA warpgroup goes 96 -> 32 (8192 registers) and the four softmax warpgroups 96 -> 112 (4 x 2048)
-  // (the request sits at the top of each role branch so that ptxas allocates registers per branch)
-#define ATTN_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 32;")
-#define ATTN_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 112;")
-#else
-#define ATTN_REG_DEC() do { } while (0)
-#define ATTN_REG_INC() do { } while (0)
-#endif
   const uint32_t tmem_S[2] = {tmem_base + 0, tmem_base + 128};
   const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
 
   if (warp == kTmaWarp) {
     // =========================== scheduler + TMA producer ===========================
-    ATTN_REG_DEC();
     if (elect_one_lane()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -335,7 +315,6 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer ===========================
-    ATTN_REG_DEC();
     if (elect_one_lane()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);  // S[128,128] = Q[128,D] K[128,D]^T
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, D, 0, 1);        // O[128,D] += P[128,128] V[128,D]
@@ -369,12 +348,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t v_lo = desc_lo_mnmajor(smem_u32(smem_kv + vstage * kTileBytes), kAtomBytes);
 #pragma unroll
         for (int k = 0; k < kBlockN / 16; ++k)
-#if BAGEL_ATTN_HALFROW   // P: keys 0-63 over S columns [0,32) (first softmax group), keys 64-127 over S columns [64,96) (second group)
-          umma_ts_lo(tmem_O[t], tmem_S[t] + (k < 4 ? k * 8 : 64 + (k - 4) * 8), v_lo + (uint32_t)(k * (2048 >> 4)), idesc_pv,
-                     (accumulate || k != 0) ? 1u : 0u);
-#else
           umma_ts_lo(tmem_O[t], tmem_S[t] + k * 8, v_lo + (uint32_t)(k * (2048 >> 4)), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-#endif
       };
 
       while (true) {
@@ -440,201 +414,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (w.nblk_t[t] > 0) ++icnt[t];
       }
     }
-  } else if (warp > kMmaWarp) {
-    ATTN_REG_DEC();   // idle warps completing the TMA / MMA warpgroup
   } else {
-    ATTN_REG_INC();
-#if BAGEL_ATTN_HALFROW
-    // =========================== softmax / correction / epilogue: two threads per query row ===========================
-    // Same protocol as the one-thread-per-row code below; what differs: a thread owns 64 of the 128 score columns of a block
-    // (P goes to the first 32 columns of its own 64), the two warps that share a lane quarter of a tile agree on the redo path
-    // through a 64-thread named barrier and exchange row maxima / row sums through shared memory, and each rescales / writes
-    // out its half of the O columns. (Validated first in csrc/attn3.cu.)
-    const int t = warp / kSoftWarps;                 // which query tile
-    const int half = (warp >> 2) & 1;                // 0: keys 0-63 of a block, 1: keys 64-127
-    const int quarter = warp & 3;                    // TMEM lane quarter accessible to this warp
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    constexpr int NC = kBlockN / 2;                  // score columns per thread
-    constexpr int DH = D / 2;                        // O columns per thread
-    const uint32_t tS = tmem_S[t] + half * NC + lane_off;
-    const uint32_t tO = tmem_O[t] + half * DH + lane_off;
-    float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512) + t * 256;          // [2 halves][128 rows]
-    volatile int* pair_flag = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 512 + 2048) + t * 8;   // [2 parity][tile][4][2]
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + quarter) : "memory"); };
-    uint32_t scnt = 0;     // S blocks consumed by this tile (parity of s_bar)
-    uint32_t icnt = 0;     // items processed by this tile (parity of o_bar)
-    int slot = 0;
-    uint32_t sphase = 0;
-
-    while (true) {
-      mbar_wait(&sched_full[slot], sphase);
-      const int item = sched_item[slot];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sched_empty[slot]);
-      if (++slot == 2) { slot = 0; sphase ^= 1; }
-      if (item >= p.num_items) break;
-      const AttnItem w = attn_decode_item(item, p);
-      if (!w.valid || (t == 1 && !w.tile1_active)) continue;
-      const int nblk = w.nblk_t[t];
-      const int Lq = w.Lq, Lk = w.Lk, shift = w.shift;
-      const int qi = w.q0 + t * kBlockM + row;
-
-      float m = -INFINITY, l = 0.f;               // m identical in both threads of a row; l = this thread's share of the row sum
-      constexpr float kRedoSum = 1073741824.0f;   // 2^30
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&s_bar[t], scnt & 1);
-        tc_fence_after();
-        const int kv0 = j * kBlockN + half * NC;   // first key of this thread's columns
-        const int tile_q_lo = w.q0 + t * kBlockM;
-        const bool need_mask = (kv0 + NC > Lk) || (p.causal && (kv0 + NC - 1 > tile_q_lo + shift));
-        const int lim = p.causal ? min(Lk - 1, qi + shift) : (Lk - 1);
-
-        uint32_t pk[NC / 2];
-        float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-        // 16 score columns at a time: at 576 threads a thread has 96 registers, and P (32 packed words) must stay in
-        // registers until the pair has agreed that the block needs no redo (the redo re-reads S, which P overwrites)
-        auto process_t = [&](auto mask_tag, auto poly_tag, const uint32_t (&v)[16], int c, float neg_ms) {
-          constexpr bool kMask = decltype(mask_tag)::value;
-          constexpr bool kPoly = decltype(poly_tag)::value && !kMask;
-          const float2 nm2 = make_float2(neg_ms, neg_ms);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
-            if constexpr (kMask) {
-              if (kv0 + c * 16 + 2 * i > lim) x0 = -INFINITY;
-              if (kv0 + c * 16 + 2 * i + 1 > lim) x1 = -INFINITY;
-            }
-            const float2 x = ffma2(make_float2(x0, x1), sc2, nm2);
-            const float2 e = (kPoly && (i & 3) == 3) ? ex2_poly2(x) : make_float2(ex2(x.x), ex2(x.y));
-            rs2[i & 1] = fadd2(rs2[i & 1], e);
-            pk[c * 8 + i] = pack_bf16x2(e.x, e.y);
-          }
-        };
-
-        const bool have_ref = __all_sync(0xffffffffu, m != -INFINITY);   // same outcome in both warps of the pair (same m)
-        bool redo = true;
-        if (have_ref) {
-          const float neg_ms = -m * p.scale_log2;
-          auto stream = [&](auto mask_tag, auto poly_tag) {
-            // a warp's TMEM load does not overlap its own math (the partner warp's does): one buffer, no double buffering
-#pragma unroll
-            for (int c = 0; c < NC / 16; ++c) {
-              uint32_t v[16];
-              tmem_ld_x16(tS + c * 16, v);
-              tmem_ld_wait();
-              process_t(mask_tag, poly_tag, v, c, neg_ms);
-            }
-          };
-          if (need_mask) stream(std::true_type{}, std::false_type{});
-          else if (p.poly) stream(std::false_type{}, std::true_type{});
-          else stream(std::false_type{}, std::false_type{});
-          const float rs_row = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
-          redo = !(rs_row <= kRedoSum);
-        }
-        const bool warp_redo = __any_sync(0xffffffffu, redo);
-        volatile int* flags = pair_flag + (scnt & 1) * 16 + quarter * 2;
-        if (lane == 0) flags[half] = warp_redo ? 1 : 0;
-        pair_sync();
-        const bool pair_redo = (flags[0] | flags[1]) != 0;
-        ++scnt;
-        float alpha = 1.0f;
-        if (pair_redo) {
-          float mx = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < NC / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_x16(tS + c * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(v[i]);
-              if (need_mask && (kv0 + c * 16 + i > lim)) x = -INFINITY;
-              mx = fmaxf(mx, x);
-            }
-          }
-          xch[half * 128 + row] = mx;
-          pair_sync();
-          mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);
-          const float m_new = fmaxf(m, mx);
-          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-          alpha = ex2((m - m_use) * p.scale_log2);   // m = -inf -> 0
-          m = m_new;
-          const float neg_ms = -m_use * p.scale_log2;
-          rs2[0] = make_float2(0.f, 0.f);
-          rs2[1] = make_float2(0.f, 0.f);
-#pragma unroll   // static pk[] indices: a run-time chunk index would push pk to local memory for the hot path too
-          for (int c = 0; c < NC / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_x16(tS + c * 16, v);
-            tmem_ld_wait();
-            if (need_mask) process_t(std::true_type{}, std::false_type{}, v, c, neg_ms);
-            else process_t(std::false_type{}, std::false_type{}, v, c, neg_ms);
-          }
-          if (j > 0) {  // O_t(j-1) is complete: S_t(j) was issued after PV_t(j-1) and the pipe is in-order
-#pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tO + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st_x32(tO + c * 32, v);
-            }
-          }
-        }
-        const float rs = (rs2[0].x + rs2[1].x) + (rs2[0].y + rs2[1].y);
-        l = l * alpha + rs;
-        tmem_st_x32(tS, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_bar[t]);
-      }
-
-      // row sum = both halves; the first barrier: the partner is past its read of a row maximum left in the same slot
-      if (nblk > 0) {
-        pair_sync();
-        xch[half * 128 + row] = l;
-        pair_sync();
-        l += xch[(half ^ 1) * 128 + row];
-        mbar_wait(&o_bar[t], icnt & 1);
-        ++icnt;
-        tc_fence_after();
-      }
-      const float inv_l = (l > 0.f && m != -INFINITY) ? (1.f / l) : 0.f;
-      const bool row_ok = qi < Lq;
-      __nv_bfloat16* orow = p.out + (long long)(w.q_beg + qi) * p.ld_out + w.h * D + half * DH;
-#pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t v[32];
-        if (nblk > 0) {
-          tmem_ld_x32(tO + c * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] = pack_bf16x2(__uint_as_float(v[q4 * 8 + 2 * e]) * inv_l, __uint_as_float(v[q4 * 8 + 2 * e + 1]) * inv_l);
-            dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-      if (nblk > 0) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[t]);
-      }
-    }
-#else
     // =========================== softmax / correction / epilogue ===========================
     const int t = warp / kSoftWarps;                 // which query tile this warp group serves
     const int quarter = warp & 3;                    // TMEM lane quarter accessible to this warp
@@ -847,7 +627,6 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(&o_free[t]);
       }
     }
-#endif
   }
 
   tc_fence_before();
