@@ -176,7 +176,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
 
-      if constexpr (EPI == EPI_SWIGLU) {
+      if constexpr (EPI == EPI_QKV) {
+        // fused q/k-norm + RoPE + K/V placement: each CTA's accumulator holds its own 128 rows x the pair's 256 columns = two
+        // whole heads, exactly the tile the 1-CTA kernel's epilogue works on (gemm_params.h)
+        qkv_epilogue_row(p, t_acc, n_blk, row_ok, out_row);
+      } else if constexpr (EPI == EPI_SWIGLU) {
         // W rows are interleaved per 256 (128 gate | 128 up): columns [0,128) of the tile = gate (staged by the leader),
         // [128,256) = up (staged by the peer) of the same 128 output features
         const int n_out0 = n_blk * (BN / 2);
@@ -291,7 +295,11 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 bool gemm2_supported(int M, int N, int K, int epilogue) {
   static const int mode = [] { const char* e = getenv("BAGEL_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   if (!mode) return false;
-  if (epilogue != EPI_BIAS && epilogue != EPI_RESID && epilogue != EPI_SWIGLU) return false;
+  // the fused-QKV epilogue on the pair kernel passes every test but measured 0.6 % SLOWER per denoising step than the 1-CTA kernel
+  // on one box (763.4 / 767.9 / 763.7 ms for off / on / off, profiles/r02_gemm_pair_ab.txt (6)) -> opt-in
+  static const int qkv = [] { const char* e = getenv("BAGEL_GEMM_PAIR_QKV"); return e ? atoi(e) : 0; }();
+  if (epilogue == EPI_QKV && !qkv) return false;
+  if (epilogue != EPI_BIAS && epilogue != EPI_RESID && epilogue != EPI_SWIGLU && epilogue != EPI_QKV) return false;
   return M >= 4 * BM && (N % kPairBN) == 0 && K >= BK;
 }
 
@@ -330,7 +338,7 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
   }
   // epilogue through shared memory + bulk tensor stores unless the output rows are scattered (row_map)
   static const bool tma_store_on = [] { const char* e = getenv("BAGEL_GEMM_TMA_STORE"); return !(e && atoi(e) == 0); }();
-  p.tma_store = (tma_store_on && p.row_map == nullptr) ? 1 : 0;
+  p.tma_store = (tma_store_on && p.row_map == nullptr && epilogue != EPI_QKV) ? 1 : 0;   // the QKV epilogue writes q / K / V rows itself
   CUtensorMap tmC{};
   if (p.tma_store) {
     const uint64_t out_cols = epilogue == EPI_SWIGLU ? (uint64_t)p.N / 2 : (uint64_t)p.N;
@@ -340,6 +348,7 @@ int gemm2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, i
     case EPI_BIAS: return launch2<EPI_BIAS>(tmA, tmB, tmC, p, stream);
     case EPI_RESID: return launch2<EPI_RESID>(tmA, tmB, tmC, p, stream);
     case EPI_SWIGLU: return launch2<EPI_SWIGLU>(tmA, tmB, tmC, p, stream);
+    case EPI_QKV: return launch2<EPI_QKV>(tmA, tmB, tmC, p, stream);
     default: return set_error(BAGEL_ERR_ARG, "gemm2: unsupported epilogue %d", epilogue);
   }
 }

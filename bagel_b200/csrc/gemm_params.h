@@ -99,4 +99,84 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 
+// Fused QKV epilogue of ONE token row (thread = row) over a 256-wide accumulator tile = two heads of 128: everything the
+// reference does between the projection and flash-attn (qwen2_navit.py:518-519 / 542-574) on the fp32 accumulators —
+// bf16(acc + bias), per-head RMSNorm with expert-routed weights, RoPE, bf16 cast, q / K / V rows written to their final
+// places. Shared by the 1-CTA kernel (gemm.cu) and the CTA-pair kernel (gemm2.cu): in both a thread of the epilogue warps owns
+// one row of its CTA's 128 x 256 accumulator tile at TMEM address t_acc.
+__device__ __forceinline__ void qkv_epilogue_row(const GemmParams& p, uint32_t t_acc, int n_blk, bool row_ok, long long out_row) {
+  const QkvEpi& e = p.qkv;
+  const bool gen = row_ok && e.expert != nullptr && e.qw1 != nullptr && e.expert[out_row];
+  const long long kv_row = (row_ok && e.kv_rows != nullptr) ? (long long)e.kv_rows[out_row] : out_row;
+#pragma unroll 1
+  for (int hh = 0; hh < 2; ++hh) {
+    const int head = n_blk * 2 + hh;
+    float x[128];
+    {
+      uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(t_acc + hh * 128 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&xr[c * 32]));
+      tmem_ld_wait();
+    }
+    if (!row_ok) continue;
+    // q/k/v_proj output as the reference sees it: bf16(acc + bias)
+    const __nv_bfloat16* bh = p.bias + head * 128;
+#pragma unroll
+    for (int i = 0; i < 128; i += 2) {
+      const uint32_t bb = *reinterpret_cast<const uint32_t*>(bh + i);
+      x[i] = bf16_round(x[i] + bf16_lo(bb));
+      x[i + 1] = bf16_round(x[i + 1] + bf16_hi(bb));
+    }
+    __nv_bfloat16* dst;
+    const bool is_v = head >= e.Hq + e.Hk;
+    if (head < e.Hq) dst = e.q_out + out_row * e.ld_q + head * 128;
+    else if (!is_v) dst = e.k_out + kv_row * e.ld_kv + (head - e.Hq) * 128;
+    else dst = e.v_out + kv_row * e.ld_kv + (head - e.Hq - e.Hk) * 128;
+    if (!is_v) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) ss += x[i] * x[i];
+      const float r = rsqrtf(ss * (1.0f / 128.0f) + e.eps);
+      const void* w = (head < e.Hq) ? (gen ? e.qw1 : e.qw0) : (gen ? e.kw1 : e.kw0);
+      const bool wf32 = e.fp32_flow >= 2;
+      const float* cs = e.cos_t + out_row * 64;
+      const float* sn = e.sin_t + out_row * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + i);
+        const float4 s4 = *reinterpret_cast<const float4*>(sn + i);
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float wa = wf32 ? static_cast<const float*>(w)[i + u]
+                                : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[i + u]);
+          const float wb = wf32 ? static_cast<const float*>(w)[64 + i + u]
+                                : __bfloat162float(static_cast<const __nv_bfloat16*>(w)[64 + i + u]);
+          float ya, yb, oa, ob;
+          if (e.fp32_flow) {
+            const float na = (e.fp32_flow == 2) ? bf16_round(x[i + u] * r) : __fmul_rn(x[i + u], r);
+            const float nb = (e.fp32_flow == 2) ? bf16_round(x[64 + i + u] * r) : __fmul_rn(x[64 + i + u], r);
+            ya = __fmul_rn(wa, na);
+            yb = __fmul_rn(wb, nb);
+            oa = __fadd_rn(__fmul_rn(ya, cc[u]), __fmul_rn(-yb, sv[u]));
+            ob = __fadd_rn(__fmul_rn(yb, cc[u]), __fmul_rn(ya, sv[u]));
+          } else {
+            ya = bf16_round(wa * bf16_round(x[i + u] * r));
+            yb = bf16_round(wb * bf16_round(x[64 + i + u] * r));
+            oa = bf16_round(ya * cc[u]) + bf16_round(-yb * sv[u]);
+            ob = bf16_round(yb * cc[u]) + bf16_round(ya * sv[u]);
+          }
+          x[i + u] = oa;
+          x[64 + i + u] = ob;
+        }
+      }
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      d4[q] = make_uint4(pack_bf16x2(x[8 * q], x[8 * q + 1]), pack_bf16x2(x[8 * q + 2], x[8 * q + 3]),
+                         pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), pack_bf16x2(x[8 * q + 6], x[8 * q + 7]));
+  }
+}
+
 }  // namespace bagel
