@@ -18,6 +18,12 @@
 //   warp 9      MMA issuer (one lane), software-pipelined over the stream of key blocks ACROSS work items
 // TMEM (512 columns): S[0] [0,128)  S[1] [128,256)  O[0] [256,256+D)  O[1] [384,384+D).
 //
+// STATUS: experimental, off by default (BAGEL_ATTN_V3=1 / BAGEL_ATTN_QT=1). Correct — tests/test_gpu_kernels.py runs the attention
+// and the adversarial lazy-rescale cases against it in a child process — but 10-20 % slower than the two-tile kernel in every
+// variant measured (profiles/r02_attn_v3_ab.txt, r02_elect_sync_ab.txt): with one tile per CTA every K/V block feeds half as many
+// MMAs, and a warp's TMEM loads do not overlap its own math (profiles/r02_microbench_tmem_mufu.txt), so the softmax stage does
+// not shrink the way the 1024-cycle MUFU bound above suggests. It is the starting point for a CTA-pair version that shares K/V.
+//
 // Same interface, masking rules and numerics as attn_varlen_kernel (attn.cu); reference seam: flash_attn_varlen_func at
 // modeling/bagel/qwen2_navit.py:361-370, 579-588 and modeling/bagel/siglip_navit.py:232-241.
 #include <cuda.h>
